@@ -1,0 +1,301 @@
+"""ctypes binding of libgmsb.so (include/gmsb.h).
+
+This is plumbing for tests, bench.py and Python users; the product is the CUDA library.  There is no fallback:
+if the shared library is missing or no CUDA device is usable, calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libgmsb.so")
+
+TC_VARIANTS = {"auto": 0, "merge": 1, "gallop": 2, "bitmap": 3}
+SIM_METRICS = {"jaccard": 0, "overlap": 1, "adamic_adar": 2, "resource": 3, "comm_neigh": 4, "total_neigh": 5,
+               "pref_att": 6}
+
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
+_u64p = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
+_f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+
+
+class GmsbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"gmsb error {code}: {msg}")
+        self.code = code
+
+
+class TcOptions(C.Structure):
+    _fields_ = [("variant", C.c_int32), ("part_index", C.c_int32), ("part_count", C.c_int32),
+                ("reuse_plan", C.c_int32), ("hub_bitmap_bits", C.c_int32), ("gallop_ratio", C.c_int32),
+                ("hub_min_work", C.c_int64), ("reserved", C.c_int32 * 4)]
+
+
+class TcStats(C.Structure):
+    _fields_ = [("triangles", C.c_uint64), ("algorithmic_bytes", C.c_uint64), ("wedges_checked", C.c_uint64),
+                ("oriented_edges", C.c_int64), ("edges_bitmap", C.c_int64), ("edges_merge", C.c_int64),
+                ("edges_gallop", C.c_int64), ("ms_orient", C.c_double), ("ms_count", C.c_double),
+                ("ms_bitmap", C.c_double), ("ms_merge", C.c_double), ("ms_gallop", C.c_double),
+                ("launches", C.c_int32), ("max_dplus", C.c_int32), ("bytes_bitmap", C.c_uint64),
+                ("bytes_light", C.c_uint64), ("wedges_bitmap", C.c_uint64), ("bitmap_items", C.c_int64),
+                ("bitmap_smem_bytes", C.c_int32), ("reserved", C.c_int32)]
+
+    def as_dict(self):
+        return {name: getattr(self, name) for name, _ in self._fields_}
+
+
+# every symbol include/gmsb.h declares: name -> (restype, argtypes)
+SIGNATURES = {
+    "gmsb_last_error": (C.c_char_p, []),
+    "gmsb_version": (C.c_int, []),
+    "gmsb_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "gmsb_set_device": (C.c_int, [C.c_int]),
+    "gmsb_set_stream": (C.c_int, [C.c_void_p]),
+    "gmsb_synchronize": (C.c_int, []),
+    "gmsb_launch_count": (C.c_int, [C.POINTER(C.c_uint64)]),
+    "gmsb_generate_rmat": (C.c_int, [C.c_int, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_int, _i32p, _i32p]),
+    "gmsb_generate_uniform": (C.c_int, [C.c_int, C.c_int64, _i32p, _i32p]),
+    "gmsb_graph_from_csr": (C.c_int, [C.c_int64, _i64p, _i32p, C.c_int, C.POINTER(C.c_void_p)]),
+    "gmsb_graph_from_csr_device": (C.c_int, [C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "gmsb_graph_from_edgelist": (C.c_int, [C.c_int64, _i32p, _i32p, C.c_int, C.POINTER(C.c_void_p)]),
+    "gmsb_graph_from_edgelist_device": (C.c_int, [C.c_int64, C.c_void_p, C.c_void_p, C.c_int,
+                                                  C.POINTER(C.c_void_p)]),
+    "gmsb_graph_relabel_by_degree": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "gmsb_graph_num_nodes": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "gmsb_graph_num_slots": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "gmsb_graph_is_directed": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "gmsb_graph_export_csr": (C.c_int, [C.c_void_p, _i64p, _i32p]),
+    "gmsb_graph_free": (C.c_int, [C.c_void_p]),
+    "gmsb_order_degree": (C.c_int, [C.c_void_p, C.c_int, _i32p]),
+    "gmsb_order_degeneracy": (C.c_int, [C.c_void_p, _i32p]),
+    "gmsb_orient": (C.c_int, [C.c_void_p, _i32p, C.POINTER(C.c_void_p)]),
+    "gmsb_tc_total": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "gmsb_tc_total_ex": (C.c_int, [C.c_void_p, C.POINTER(TcOptions), C.POINTER(C.c_uint64), C.POINTER(TcStats)]),
+    "gmsb_tc_vertex2": (C.c_int, [C.c_void_p, _i64p]),
+    "gmsb_intersect_count_batch": (C.c_int, [C.c_void_p, C.c_int64, _i32p, _i32p, _u64p]),
+    "gmsb_intersect_batch": (C.c_int, [C.c_void_p, C.c_int64, _i32p, _i32p, _i64p, C.c_void_p, C.c_int64]),
+    "gmsb_pair_similarity": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, _i32p, _i32p, _f64p]),
+    "gmsb_edge_similarity": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int64)]),
+    "gmsb_kclique_count": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]),
+    "gmsb_kclique_count_ordered": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load libgmsb.so; raises if it has not been built (python -c 'import __graft_entry__ as g; g.build()')."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: build it with `make -C gms_b200/csrc` "
+                              "(gms-b200 has no CPU fallback)")
+        dll = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            f = getattr(dll, name)
+            f.restype, f.argtypes = res, args
+        _lib = dll
+    return _lib
+
+
+def _check(code):
+    if code != 0:
+        raise GmsbError(code, lib().gmsb_last_error().decode())
+
+
+def device_count():
+    c = C.c_int(0)
+    _check(lib().gmsb_device_count(C.byref(c)))
+    return c.value
+
+
+def set_device(i):
+    _check(lib().gmsb_set_device(i))
+
+
+def set_stream(ptr):
+    _check(lib().gmsb_set_stream(ptr))
+
+
+def synchronize():
+    _check(lib().gmsb_synchronize())
+
+
+def launch_count():
+    c = C.c_uint64(0)
+    _check(lib().gmsb_launch_count(C.byref(c)))
+    return c.value
+
+
+def generate_rmat(scale, m=None, a=0.57, b=0.19, c=0.19, permute=True, degree=16):
+    """Reference generator semantics (gapbs/generator.h:81-114); defaults = `-g kronecker <scale> --deg 16`."""
+    m = (1 << scale) * degree if m is None else m
+    src, dst = np.zeros(max(m, 1), np.int32), np.zeros(max(m, 1), np.int32)
+    _check(lib().gmsb_generate_rmat(scale, m, a, b, c, int(permute), src, dst))
+    return src[:m], dst[:m]
+
+
+def generate_uniform(scale, m=None, degree=16):
+    m = (1 << scale) * degree if m is None else m
+    src, dst = np.zeros(max(m, 1), np.int32), np.zeros(max(m, 1), np.int32)
+    _check(lib().gmsb_generate_uniform(scale, m, src, dst))
+    return src[:m], dst[:m]
+
+
+def _ids(x):
+    x = np.ascontiguousarray(x, np.int32)
+    return x if len(x) else np.zeros(1, np.int32)
+
+
+class Graph:
+    """A device-resident CSR graph (the SGraph of the reference's algorithms)."""
+
+    def __init__(self, handle):
+        self.h = C.c_void_p(handle) if not isinstance(handle, C.c_void_p) else handle
+
+    # --- construction
+    @staticmethod
+    def from_csr(offsets, nbrs, directed=False):
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        n = len(offsets) - 1
+        nn = len(nbrs)
+        h = C.c_void_p()
+        _check(lib().gmsb_graph_from_csr(n, offsets, _ids(nbrs), int(directed), C.byref(h)))
+        assert nn >= offsets[-1]
+        return Graph(h)
+
+    @staticmethod
+    def from_csr_device(n, offsets_ptr, nbrs_ptr, directed=False):
+        h = C.c_void_p()
+        _check(lib().gmsb_graph_from_csr_device(n, offsets_ptr, nbrs_ptr, int(directed), C.byref(h)))
+        return Graph(h)
+
+    @staticmethod
+    def from_edgelist(src, dst, symmetrize=True):
+        assert len(src) == len(dst)
+        h = C.c_void_p()
+        _check(lib().gmsb_graph_from_edgelist(len(src), _ids(src), _ids(dst), int(symmetrize), C.byref(h)))
+        return Graph(h)
+
+    @staticmethod
+    def from_edgelist_device(m, src_ptr, dst_ptr, symmetrize=True):
+        h = C.c_void_p()
+        _check(lib().gmsb_graph_from_edgelist_device(m, src_ptr, dst_ptr, int(symmetrize), C.byref(h)))
+        return Graph(h)
+
+    def free(self):
+        if self.h:
+            lib().gmsb_graph_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    # --- properties
+    @property
+    def n(self):
+        v = C.c_int64(0)
+        _check(lib().gmsb_graph_num_nodes(self.h, C.byref(v)))
+        return v.value
+
+    @property
+    def slots(self):
+        v = C.c_int64(0)
+        _check(lib().gmsb_graph_num_slots(self.h, C.byref(v)))
+        return v.value
+
+    @property
+    def directed(self):
+        v = C.c_int(0)
+        _check(lib().gmsb_graph_is_directed(self.h, C.byref(v)))
+        return bool(v.value)
+
+    def export_csr(self):
+        off = np.zeros(self.n + 1, np.int64)
+        nbr = np.zeros(max(self.slots, 1), np.int32)
+        _check(lib().gmsb_graph_export_csr(self.h, off, nbr))
+        return off, nbr[:off[-1]]
+
+    # --- transforms / orderings
+    def relabel_by_degree(self):
+        h = C.c_void_p()
+        _check(lib().gmsb_graph_relabel_by_degree(self.h, C.byref(h)))
+        return Graph(h)
+
+    def degree_order(self, rank_format=False):
+        out = np.zeros(max(self.n, 1), np.int32)
+        _check(lib().gmsb_order_degree(self.h, int(rank_format), out))
+        return out[:self.n]
+
+    def degeneracy_rank(self):
+        out = np.zeros(max(self.n, 1), np.int32)
+        _check(lib().gmsb_order_degeneracy(self.h, out))
+        return out[:self.n]
+
+    def orient(self, ranking):
+        h = C.c_void_p()
+        _check(lib().gmsb_orient(self.h, _ids(ranking), C.byref(h)))
+        return Graph(h)
+
+    # --- triangles
+    def tc_total(self):
+        out = C.c_uint64(0)
+        _check(lib().gmsb_tc_total(self.h, C.byref(out)))
+        return out.value
+
+    def tc_total_ex(self, variant="auto", part_index=0, part_count=1, reuse_plan=False, hub_bitmap_bits=0,
+                    gallop_ratio=0, hub_min_work=0):
+        opt = TcOptions(TC_VARIANTS[variant], part_index, part_count, int(reuse_plan), hub_bitmap_bits, gallop_ratio,
+                        hub_min_work)
+        out, st = C.c_uint64(0), TcStats()
+        _check(lib().gmsb_tc_total_ex(self.h, C.byref(opt), C.byref(out), C.byref(st)))
+        return out.value, st.as_dict()
+
+    def tc_vertex2(self):
+        out = np.zeros(max(self.n, 1), np.int64)
+        _check(lib().gmsb_tc_vertex2(self.h, out))
+        return out[:self.n]
+
+    # --- set algebra / similarity
+    def intersect_count_batch(self, a, b):
+        assert len(a) == len(b)
+        out = np.zeros(max(len(a), 1), np.uint64)
+        _check(lib().gmsb_intersect_count_batch(self.h, len(a), _ids(a), _ids(b), out))
+        return out[:len(a)]
+
+    def intersect_batch(self, a, b):
+        assert len(a) == len(b)
+        off = np.zeros(len(a) + 1, np.int64)
+        _check(lib().gmsb_intersect_batch(self.h, len(a), _ids(a), _ids(b), off, None, 0))
+        elems = np.zeros(max(int(off[-1]), 1), np.int32)
+        _check(lib().gmsb_intersect_batch(self.h, len(a), _ids(a), _ids(b), off, elems.ctypes.data, len(elems)))
+        return off, elems[:off[-1]]
+
+    def pair_similarity(self, metric, a, b):
+        assert len(a) == len(b)
+        out = np.zeros(max(len(a), 1), np.float64)
+        _check(lib().gmsb_pair_similarity(self.h, SIM_METRICS[metric], len(a), _ids(a), _ids(b), out))
+        return out[:len(a)]
+
+    def edge_similarity(self, metric):
+        m = C.c_int64(0)
+        _check(lib().gmsb_edge_similarity(self.h, SIM_METRICS[metric], None, C.byref(m)))
+        out = np.zeros(max(m.value, 1), np.float64)
+        _check(lib().gmsb_edge_similarity(self.h, SIM_METRICS[metric], out.ctypes.data, C.byref(m)))
+        return out[:m.value]
+
+    # --- cliques
+    def kclique_count(self, k):
+        out = C.c_uint64(0)
+        _check(lib().gmsb_kclique_count(self.h, k, C.byref(out)))
+        return out.value
+
+    def kclique_count_ordered(self, k):
+        out = C.c_uint64(0)
+        _check(lib().gmsb_kclique_count_ordered(self.h, k, C.byref(out)))
+        return out.value

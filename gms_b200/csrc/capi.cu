@@ -1,0 +1,259 @@
+// capi.cu — the extern "C" boundary declared in include/gmsb.h.  Every entry point catches C++ exceptions,
+// records the message for gmsb_last_error() and maps it to a negative status; nothing here computes on the CPU.
+#include "common.cuh"
+#include "orient.cuh"
+#include "ops.cuh"
+
+#include <cstring>
+#include <mutex>
+
+namespace gmsb {
+
+namespace {
+thread_local std::string g_last_error;
+Runtime g_rt;
+bool g_rt_ready = false;
+int g_device = 0;
+std::mutex g_rt_mutex;
+}  // namespace
+
+void set_last_error(const std::string &msg) { g_last_error = msg; }
+
+Runtime &rt() {
+    if (!g_rt_ready) {
+        std::lock_guard<std::mutex> lock(g_rt_mutex);
+        if (!g_rt_ready) {
+            int count = 0;
+            cudaError_t e = cudaGetDeviceCount(&count);
+            if (e != cudaSuccess || count == 0)
+                throw Error(GMSB_ERR_CUDA, std::string("no usable CUDA device (") +
+                                               (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                                               "); gms-b200 has no CPU fallback");
+            GMSB_CUDA(cudaSetDevice(g_device));
+            cudaDeviceProp prop{};
+            GMSB_CUDA(cudaGetDeviceProperties(&prop, g_device));
+            g_rt.device = g_device;
+            g_rt.sm_count = prop.multiProcessorCount;
+            g_rt.smem_optin = prop.sharedMemPerBlockOptin;
+            g_rt_ready = true;
+        }
+    }
+    return g_rt;
+}
+
+template <typename F>
+int guarded(F &&f) {
+    try {
+        f();
+        return GMSB_OK;
+    } catch (const Error &e) {
+        set_last_error(e.what());
+        return e.code;
+    } catch (const std::bad_alloc &) {
+        set_last_error("host allocation failed");
+        return GMSB_ERR_OOM;
+    } catch (const std::exception &e) {
+        set_last_error(e.what());
+        return GMSB_ERR_INVALID;
+    }
+}
+
+inline Graph &G(gmsb_graph_t h) {
+    GMSB_REQUIRE(h != nullptr, "null graph handle");
+    return *reinterpret_cast<Graph *>(h);
+}
+
+}  // namespace gmsb
+
+using namespace gmsb;
+
+extern "C" {
+
+GMSB_API const char *gmsb_last_error(void) { return g_last_error.c_str(); }
+GMSB_API int gmsb_version(void) { return 100; }
+
+GMSB_API int gmsb_device_count(int *count) {
+    return guarded([&] {
+        GMSB_REQUIRE(count, "null argument");
+        cudaError_t e = cudaGetDeviceCount(count);
+        if (e != cudaSuccess) { *count = 0; throw Error(GMSB_ERR_CUDA, cudaGetErrorString(e)); }
+    });
+}
+
+GMSB_API int gmsb_set_device(int device) {
+    return guarded([&] {
+        GMSB_REQUIRE(device >= 0, "negative device index");
+        g_device = device;
+        if (g_rt_ready) {
+            GMSB_CUDA(cudaSetDevice(device));
+            cudaDeviceProp prop{};
+            GMSB_CUDA(cudaGetDeviceProperties(&prop, device));
+            g_rt.device = device;
+            g_rt.sm_count = prop.multiProcessorCount;
+            g_rt.smem_optin = prop.sharedMemPerBlockOptin;
+        } else {
+            rt();
+        }
+    });
+}
+
+GMSB_API int gmsb_set_stream(void *s) { return guarded([&] { rt().stream = reinterpret_cast<cudaStream_t>(s); }); }
+GMSB_API int gmsb_synchronize(void) { return guarded([&] { GMSB_CUDA(cudaStreamSynchronize(rt().stream)); }); }
+GMSB_API int gmsb_launch_count(uint64_t *count) {
+    return guarded([&] { GMSB_REQUIRE(count, "null argument"); *count = g_rt_ready ? g_rt.launches : 0; });
+}
+
+// ---- generators (host) -----------------------------------------------------------------------------------------
+GMSB_API int gmsb_generate_rmat(int scale, int64_t m, float a, float b, float c, int permute, int32_t *src,
+                                int32_t *dst) {
+    return guarded([&] { generate_rmat(scale, m, a, b, c, permute != 0, src, dst); });
+}
+GMSB_API int gmsb_generate_uniform(int scale, int64_t m, int32_t *src, int32_t *dst) {
+    return guarded([&] { generate_uniform(scale, m, src, dst); });
+}
+
+// ---- graphs ----------------------------------------------------------------------------------------------------
+GMSB_API int gmsb_graph_from_csr(int64_t n, const int64_t *off, const int32_t *nbr, int directed, gmsb_graph_t *out) {
+    return guarded([&] {
+        GMSB_REQUIRE(out, "null output handle");
+        *out = reinterpret_cast<gmsb_graph_t>(graph_from_csr_device(n, off, nbr, directed != 0, true));
+    });
+}
+GMSB_API int gmsb_graph_from_csr_device(int64_t n, const int64_t *off, const int32_t *nbr, int directed, gmsb_graph_t *out) {
+    return guarded([&] {
+        GMSB_REQUIRE(out, "null output handle");
+        *out = reinterpret_cast<gmsb_graph_t>(graph_from_csr_device(n, off, nbr, directed != 0, false));
+    });
+}
+GMSB_API int gmsb_graph_from_edgelist(int64_t m, const int32_t *src, const int32_t *dst, int symmetrize, gmsb_graph_t *out) {
+    return guarded([&] {
+        GMSB_REQUIRE(out, "null output handle");
+        GMSB_REQUIRE(m >= 0 && (m == 0 || (src && dst)), "graph_from_edgelist: bad arguments");
+        DevBuf<vid_t> s(m), d(m);
+        s.upload(src, m);
+        d.upload(dst, m);
+        *out = reinterpret_cast<gmsb_graph_t>(graph_from_edgelist_device(m, s.p, d.p, symmetrize != 0));
+    });
+}
+GMSB_API int gmsb_graph_from_edgelist_device(int64_t m, const int32_t *src, const int32_t *dst, int symmetrize,
+                                    gmsb_graph_t *out) {
+    return guarded([&] {
+        GMSB_REQUIRE(out, "null output handle");
+        *out = reinterpret_cast<gmsb_graph_t>(graph_from_edgelist_device(m, src, dst, symmetrize != 0));
+    });
+}
+GMSB_API int gmsb_graph_relabel_by_degree(gmsb_graph_t g, gmsb_graph_t *out) {
+    return guarded([&] {
+        GMSB_REQUIRE(out, "null output handle");
+        *out = reinterpret_cast<gmsb_graph_t>(graph_relabel_by_degree(G(g)));
+    });
+}
+GMSB_API int gmsb_graph_num_nodes(gmsb_graph_t g, int64_t *n) {
+    return guarded([&] { GMSB_REQUIRE(n, "null argument"); *n = G(g).n; });
+}
+GMSB_API int gmsb_graph_num_slots(gmsb_graph_t g, int64_t *s) {
+    return guarded([&] { GMSB_REQUIRE(s, "null argument"); *s = G(g).slots; });
+}
+GMSB_API int gmsb_graph_is_directed(gmsb_graph_t g, int *d) {
+    return guarded([&] { GMSB_REQUIRE(d, "null argument"); *d = G(g).directed ? 1 : 0; });
+}
+GMSB_API int gmsb_graph_export_csr(gmsb_graph_t g, int64_t *off, int32_t *nbr) {
+    return guarded([&] {
+        Graph &gr = G(g);
+        GMSB_REQUIRE(off && (nbr || gr.slots == 0), "null output");
+        gr.off.download(off, gr.n + 1);
+        gr.nbr.download(nbr, gr.slots);
+    });
+}
+GMSB_API int gmsb_graph_free(gmsb_graph_t g) {
+    return guarded([&] { delete reinterpret_cast<Graph *>(g); });
+}
+
+// ---- orderings -----------------------------------------------------------------------------------------------------
+GMSB_API int gmsb_order_degree(gmsb_graph_t g, int rank_format, int32_t *out) {
+    return guarded([&] {
+        Graph &gr = G(g);
+        GMSB_REQUIRE(out || gr.n == 0, "null output");
+        DevBuf<vid_t> order, rank;
+        degree_order(gr, order, rank);
+        (rank_format ? rank : order).download(out, gr.n);
+    });
+}
+GMSB_API int gmsb_order_degeneracy(gmsb_graph_t g, int32_t *out_rank) {
+    return guarded([&] {
+        Graph &gr = G(g);
+        GMSB_REQUIRE(out_rank || gr.n == 0, "null output");
+        degeneracy_rank(gr, out_rank);
+    });
+}
+GMSB_API int gmsb_orient(gmsb_graph_t g, const int32_t *ranking, gmsb_graph_t *dag) {
+    return guarded([&] {
+        GMSB_REQUIRE(dag, "null output handle");
+        *dag = reinterpret_cast<gmsb_graph_t>(induce_directed(G(g), ranking));
+    });
+}
+
+// ---- triangles -------------------------------------------------------------------------------------------------------
+GMSB_API int gmsb_tc_total_ex(gmsb_graph_t g, const gmsb_tc_options *opt, uint64_t *out, gmsb_tc_stats *stats) {
+    return guarded([&] {
+        gmsb_tc_options o{};
+        if (opt) o = *opt;
+        tc_total(G(g), o, out, stats);
+    });
+}
+GMSB_API int gmsb_tc_total(gmsb_graph_t g, uint64_t *out) {
+    gmsb_tc_options o{};
+    o.reuse_plan = 1;
+    return gmsb_tc_total_ex(g, &o, out, nullptr);
+}
+GMSB_API int gmsb_tc_vertex2(gmsb_graph_t g, int64_t *out_n) {
+    return guarded([&] {
+        Graph &gr = G(g);
+        GMSB_REQUIRE(out_n || gr.n == 0, "null output");
+        tc_vertex2(gr, out_n);
+    });
+}
+
+// ---- set algebra / similarity --------------------------------------------------------------------------------------------
+GMSB_API int gmsb_intersect_count_batch(gmsb_graph_t g, int64_t np, const int32_t *a, const int32_t *b, uint64_t *out) {
+    return guarded([&] {
+        GMSB_REQUIRE(np >= 0 && (np == 0 || (a && b && out)), "intersect_count_batch: bad arguments");
+        intersect_count_batch(G(g), np, a, b, out);
+    });
+}
+GMSB_API int gmsb_intersect_batch(gmsb_graph_t g, int64_t np, const int32_t *a, const int32_t *b, int64_t *out_offsets,
+                         int32_t *out_elems, int64_t cap) {
+    return guarded([&] {
+        GMSB_REQUIRE(np >= 0 && out_offsets && (np == 0 || (a && b)), "intersect_batch: bad arguments");
+        intersect_batch(G(g), np, a, b, out_offsets, out_elems, cap);
+    });
+}
+GMSB_API int gmsb_pair_similarity(gmsb_graph_t g, int metric, int64_t np, const int32_t *a, const int32_t *b, double *out) {
+    return guarded([&] {
+        GMSB_REQUIRE(np >= 0 && (np == 0 || (a && b && out)), "pair_similarity: bad arguments");
+        GMSB_REQUIRE(metric >= 0 && metric <= GMSB_SIM_PREF_ATT, "invalid similarity measure");
+        pair_similarity(G(g), metric, np, a, b, out);
+    });
+}
+GMSB_API int gmsb_edge_similarity(gmsb_graph_t g, int metric, double *out, int64_t *m_out) {
+    return guarded([&] {
+        GMSB_REQUIRE(metric >= 0 && metric <= GMSB_SIM_PREF_ATT, "invalid similarity measure");
+        edge_similarity(G(g), metric, out, m_out);
+    });
+}
+
+// ---- cliques -----------------------------------------------------------------------------------------------------------------
+GMSB_API int gmsb_kclique_count(gmsb_graph_t g, int k, uint64_t *out) {
+    return guarded([&] {
+        GMSB_REQUIRE(out && k >= 1, "kclique_count: bad arguments");
+        kclique_count(G(g), k, out);
+    });
+}
+GMSB_API int gmsb_kclique_count_ordered(gmsb_graph_t g, int k, uint64_t *out) {
+    return guarded([&] {
+        GMSB_REQUIRE(out && k >= 1, "kclique_count_ordered: bad arguments");
+        kclique_count_ordered(G(g), k, out);
+    });
+}
+
+}  // extern "C"

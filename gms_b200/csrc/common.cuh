@@ -1,0 +1,125 @@
+// common.cuh — runtime plumbing shared by every translation unit of libgmsb.so:
+// error handling, the per-process stream, launch accounting and an RAII device buffer.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <utility>
+
+#include "../../include/gmsb.h"
+
+namespace gmsb {
+
+using vid_t = int32_t;     // vertex id (gms/common/types.h:9)
+using eid_t = int64_t;     // CSR offset
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+
+#define GMSB_CUDA(expr)                                                                                  \
+    do {                                                                                                 \
+        cudaError_t e_ = (expr);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            throw ::gmsb::Error(e_ == cudaErrorMemoryAllocation ? GMSB_ERR_OOM : GMSB_ERR_CUDA,          \
+                                std::string(#expr) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ +   \
+                                    ":" + std::to_string(__LINE__) + ")");                               \
+        }                                                                                                \
+    } while (0)
+
+#define GMSB_REQUIRE(cond, msg)                                        \
+    do {                                                               \
+        if (!(cond)) throw ::gmsb::Error(GMSB_ERR_INVALID, (msg));     \
+    } while (0)
+
+struct Runtime {
+    cudaStream_t stream = nullptr;
+    uint64_t launches = 0;
+    int sm_count = 0;
+    int device = -1;
+    size_t smem_optin = 0;
+};
+Runtime &rt();             // lazily initialised; throws GMSB_ERR_CUDA when no device is usable
+void set_last_error(const std::string &msg);
+
+// Count a kernel launch (bench.py reports the total as gpu_launches) and surface launch errors early.
+inline void launched() {
+    rt().launches++;
+    GMSB_CUDA(cudaPeekAtLastError());
+}
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    explicit DevBuf(size_t count) { alloc(count); }
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf &operator=(DevBuf &&o) noexcept {
+        if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+        return *this;
+    }
+    ~DevBuf() { release(); }
+    void alloc(size_t count) {
+        release();
+        n = count;
+        if (count) GMSB_CUDA(cudaMalloc(&p, count * sizeof(T)));
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+    }
+    void zero() { if (n) GMSB_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), rt().stream)); }
+    void upload(const T *host, size_t count) {
+        if (count) GMSB_CUDA(cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, rt().stream));
+    }
+    void download(T *host, size_t count) const {
+        if (count) GMSB_CUDA(cudaMemcpyAsync(host, p, count * sizeof(T), cudaMemcpyDeviceToHost, rt().stream));
+        GMSB_CUDA(cudaStreamSynchronize(rt().stream));
+    }
+    T get(size_t i) const {
+        T v;
+        GMSB_CUDA(cudaMemcpyAsync(&v, p + i, sizeof(T), cudaMemcpyDeviceToHost, rt().stream));
+        GMSB_CUDA(cudaStreamSynchronize(rt().stream));
+        return v;
+    }
+};
+
+// Device timer on the library's stream.
+struct DevTimer {
+    cudaEvent_t a = nullptr, b = nullptr;
+    DevTimer() { cudaEventCreate(&a); cudaEventCreate(&b); }
+    ~DevTimer() { cudaEventDestroy(a); cudaEventDestroy(b); }
+    void start() { cudaEventRecord(a, rt().stream); }
+    void stop() { cudaEventRecord(b, rt().stream); }
+    double ms() {
+        cudaEventSynchronize(b);
+        float t = 0;
+        cudaEventElapsedTime(&t, a, b);
+        return t;
+    }
+};
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline int bits_for(uint64_t x) { int b = 0; while (b < 64 && (x >> b)) ++b; return b ? b : 1; }
+
+// ---- device graph ----------------------------------------------------------------------------------------------
+struct TcPlan;      // tc.cu
+struct Dag;         // orient.cu
+
+struct Graph {
+    int64_t n = 0;
+    int64_t slots = 0;          // CSR entries
+    bool directed = false;
+    DevBuf<eid_t> off;          // n+1
+    DevBuf<vid_t> nbr;          // slots, ascending within each list
+    Dag *dag = nullptr;         // cached degree-oriented DAG (undirected graphs only)
+    ~Graph();
+};
+
+}  // namespace gmsb

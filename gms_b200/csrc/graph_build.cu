@@ -1,0 +1,196 @@
+// graph_build.cu — device-resident CSR construction.
+//
+// Replaces, on the GPU:
+//   BuilderBase::MakeGraphFromEL + SquishGraph   gms/third_party/gapbs/builder.h:279-298,206-251
+//   BuilderBase::RelabelByDegree                 gms/third_party/gapbs/builder.h:1699-1735
+//   SetGraph<Set>::FromCGraph                    gms/representations/graphs/set_graph.h:153-181
+//
+// Design: the reference scatters edges with fetch_and_add and then sorts every list on the CPU.  Here the whole
+// edge multiset is one array of 64-bit keys (u<<32 | v); a single LSD radix sort over only the significant bits
+// puts it in CSR order, duplicates and self loops are dropped by a flag + scan compaction, and the offsets
+// fall out of a degree histogram + scan.  All passes are streaming and HBM-bound.
+#include "common.cuh"
+#include "sort.cuh"
+#include "isect.cuh"
+
+namespace gmsb {
+
+namespace {
+
+__global__ void k_max_id(const vid_t *__restrict__ a, const vid_t *__restrict__ b, int64_t m, int *out) {
+    int mx = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x)
+        mx = max(mx, max(a[i], b[i]));
+    for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, mx);
+}
+
+__global__ void k_min_id(const vid_t *__restrict__ a, const vid_t *__restrict__ b, int64_t m, int *out) {
+    int mn = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x)
+        mn = min(mn, min(a[i], b[i]));
+    for (int o = 16; o; o >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    if ((threadIdx.x & 31) == 0) atomicMin(out, mn);
+}
+
+__global__ void k_make_keys(const vid_t *__restrict__ src, const vid_t *__restrict__ dst, int64_t m, bool sym,
+                            uint64_t *__restrict__ keys) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t u = (uint32_t)src[i], v = (uint32_t)dst[i];
+        keys[i] = (u << 32) | v;
+        if (sym) keys[m + i] = (v << 32) | u;
+    }
+}
+
+// keep[i] = 1 for the first copy of each (u,v) with u != v; also histogram kept entries per source vertex.
+__global__ void k_flag_unique(const uint64_t *__restrict__ keys, int64_t K, uint8_t *__restrict__ keep,
+                              unsigned long long *__restrict__ deg /* n+1, counts land at [u+1] */) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < K; i += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t k = keys[i];
+        uint32_t u = (uint32_t)(k >> 32), v = (uint32_t)k;
+        bool kp = (u != v) && (i == 0 || keys[i - 1] != k);
+        keep[i] = kp;
+        if (kp) atomicAdd(&deg[u + 1], 1ull);
+    }
+}
+
+__global__ void k_scatter_kept(const uint64_t *__restrict__ keys, const uint8_t *__restrict__ keep,
+                               const int64_t *__restrict__ pos, int64_t K, vid_t *__restrict__ nbr) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < K; i += (int64_t)gridDim.x * blockDim.x)
+        if (keep[i]) nbr[pos[i]] = (vid_t)(uint32_t)keys[i];
+}
+
+__global__ void k_degree_keys_desc(const eid_t *__restrict__ off, int64_t n, uint64_t *__restrict__ keys) {
+    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x)
+        keys[v] = ((uint64_t)(off[v + 1] - off[v]) << 32) | (uint32_t)v;
+}
+
+// position i of the (degree desc, id desc) order holds old vertex key&0xffffffff: record new id and new degree.
+__global__ void k_newid_from_order(const uint64_t *__restrict__ sorted, int64_t n, vid_t *__restrict__ newid,
+                                   eid_t *__restrict__ newoff /* n+1 */) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t k = sorted[i];
+        newid[(uint32_t)k] = (vid_t)i;
+        newoff[i + 1] = (eid_t)(k >> 32);
+        if (i == 0) newoff[0] = 0;
+    }
+}
+
+// one warp per vertex: emit (newid[u]<<32 | newid[v]) for every slot, in place of the old slot.
+__global__ void k_relabel_keys(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, int64_t n,
+                               const vid_t *__restrict__ newid, uint64_t *__restrict__ keys) {
+    int lane = threadIdx.x & 31;
+    int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t u = warp; u < n; u += nwarps) {
+        eid_t b = off[u], e = off[u + 1];
+        uint64_t hi = (uint64_t)(uint32_t)newid[u] << 32;
+        for (eid_t s = b + lane; s < e; s += 32) keys[s] = hi | (uint32_t)newid[nbr[s]];
+    }
+}
+
+__global__ void k_low32(const uint64_t *__restrict__ keys, int64_t K, vid_t *__restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < K; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (vid_t)(uint32_t)keys[i];
+}
+
+
+}  // namespace
+
+Graph *graph_from_csr_device(int64_t n, const eid_t *off, const vid_t *nbr, bool directed, bool host_src) {
+    GMSB_REQUIRE(n >= 0 && off != nullptr, "graph_from_csr: bad arguments");
+    Runtime &r = rt();
+    auto *g = new Graph();
+    try {
+        g->n = n;
+        g->directed = directed;
+        g->off.alloc(n + 1);
+        cudaMemcpyKind kind = host_src ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+        GMSB_CUDA(cudaMemcpyAsync(g->off.p, off, sizeof(eid_t) * (n + 1), kind, r.stream));
+        eid_t first, last;
+        if (host_src) { first = off[0]; last = off[n]; }
+        else {
+            GMSB_CUDA(cudaMemcpyAsync(&first, off, sizeof(eid_t), cudaMemcpyDeviceToHost, r.stream));
+            GMSB_CUDA(cudaMemcpyAsync(&last, off + n, sizeof(eid_t), cudaMemcpyDeviceToHost, r.stream));
+            GMSB_CUDA(cudaStreamSynchronize(r.stream));
+        }
+        GMSB_REQUIRE(first == 0 && last >= 0, "graph_from_csr: offsets must start at 0 and be non-negative");
+        GMSB_REQUIRE(last == 0 || nbr != nullptr, "graph_from_csr: null neighbour array");
+        g->slots = last;
+        g->nbr.alloc(last);
+        if (last) GMSB_CUDA(cudaMemcpyAsync(g->nbr.p, nbr, sizeof(vid_t) * last, kind, r.stream));
+        GMSB_CUDA(cudaStreamSynchronize(r.stream));
+    } catch (...) { delete g; throw; }
+    return g;
+}
+
+Graph *graph_from_edgelist_device(int64_t m, const vid_t *src, const vid_t *dst, bool symmetrize) {
+    GMSB_REQUIRE(m >= 0 && (m == 0 || (src && dst)), "graph_from_edgelist: bad arguments");
+    Runtime &r = rt();
+    auto *g = new Graph();
+    try {
+        g->directed = !symmetrize;
+        int mx = 0;
+        if (m) {
+            DevBuf<int> d_ext(2);
+            d_ext.zero();
+            k_max_id<<<grid_for(m, 256), 256, 0, r.stream>>>(src, dst, m, d_ext.p); launched();
+            k_min_id<<<grid_for(m, 256), 256, 0, r.stream>>>(src, dst, m, d_ext.p + 1); launched();
+            mx = d_ext.get(0);
+            GMSB_REQUIRE(d_ext.get(1) >= 0, "graph_from_edgelist: negative vertex id");
+        }
+        int64_t n = (int64_t)mx + 1;             // FindMaxNodeId(el) + 1, builder.h:285
+        g->n = n;
+        int64_t K = symmetrize ? 2 * m : m;
+        g->off.alloc(n + 1);
+        g->off.zero();
+        if (K == 0) { g->slots = 0; GMSB_CUDA(cudaStreamSynchronize(r.stream)); return g; }
+
+        DevBuf<uint64_t> keys(K), alt(K);
+        k_make_keys<<<grid_for(m, 256), 256, 0, r.stream>>>(src, dst, m, symmetrize, keys.p); launched();
+        uint64_t *sorted = radix_sort_keys(keys.p, alt.p, K, 0, 32 + bits_for((uint64_t)mx));
+
+        DevBuf<uint8_t> keep(K);
+        k_flag_unique<<<grid_for(K, 256), 256, 0, r.stream>>>(sorted, K, keep.p,
+                                                              reinterpret_cast<unsigned long long *>(g->off.p));
+        launched();
+        DevBuf<int64_t> pos(K);
+        exclusive_sum(keep.p, pos.p, K);
+        inclusive_sum_inplace(g->off.p, n + 1);
+        g->slots = g->off.get(n);
+        g->nbr.alloc(g->slots);
+        k_scatter_kept<<<grid_for(K, 256), 256, 0, r.stream>>>(sorted, keep.p, pos.p, K, g->nbr.p); launched();
+        GMSB_CUDA(cudaStreamSynchronize(r.stream));
+    } catch (...) { delete g; throw; }
+    return g;
+}
+
+Graph *graph_relabel_by_degree(const Graph &in) {
+    GMSB_REQUIRE(!in.directed, "relabel_by_degree: cannot relabel a directed graph");   // builder.h:1702-1705
+    Runtime &r = rt();
+    auto *g = new Graph();
+    try {
+        int64_t n = in.n, K = in.slots;
+        g->n = n; g->slots = K; g->directed = false;
+        g->off.alloc(n + 1);
+        g->nbr.alloc(K);
+        if (n == 0) return g;
+        DevBuf<uint64_t> dk(n), dalt(n);
+        k_degree_keys_desc<<<grid_for(n, 256), 256, 0, r.stream>>>(in.off.p, n, dk.p); launched();
+        uint64_t *order = radix_sort_keys(dk.p, dalt.p, n, 0, 64, /*descending=*/true);
+        DevBuf<vid_t> newid(n);
+        k_newid_from_order<<<grid_for(n, 256), 256, 0, r.stream>>>(order, n, newid.p, g->off.p); launched();
+        inclusive_sum_inplace(g->off.p, n + 1);
+        if (K) {
+            DevBuf<uint64_t> keys(K), alt(K);
+            k_relabel_keys<<<grid_for(n * 32, 256), 256, 0, r.stream>>>(in.off.p, in.nbr.p, n, newid.p, keys.p);
+            launched();
+            uint64_t *sorted = radix_sort_keys(keys.p, alt.p, K, 0, 32 + bits_for((uint64_t)(n - 1)));
+            k_low32<<<grid_for(K, 256), 256, 0, r.stream>>>(sorted, K, g->nbr.p); launched();
+        }
+        GMSB_CUDA(cudaStreamSynchronize(r.stream));
+    } catch (...) { delete g; throw; }
+    return g;
+}
+
+}  // namespace gmsb

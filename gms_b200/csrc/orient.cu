@@ -1,0 +1,192 @@
+// orient.cu — vertex orderings and DAG orientation on the device.
+//
+// Replaces:
+//   PpParallel::getDegreeOrdering            gms/algorithms/preprocessing/parallel/degree.h:16-61
+//   PpSequential::InduceDirectedGraph        gms/algorithms/preprocessing/sequential/apply_order.h:10-35
+//   PpSequential::getDegeneracyOrderingDanischHeap  gms/algorithms/preprocessing/sequential/degeneracy_danisch.h:12-56
+//
+// The oriented graph lives in RANK SPACE: vertex ids are replaced by their position in the ordering, so
+// N+(u) = { w in N(u) : w > u } and every list is a suffix-closed, ascending id range.  That makes "v is a hub"
+// equivalent to "v is close to n", which is what lets the bitmap kernel (tc.cu) keep N+(v) in shared memory.
+#include "common.cuh"
+#include "sort.cuh"
+#include "isect.cuh"
+#include "orient.cuh"
+
+namespace gmsb {
+
+namespace {
+
+
+__global__ void k_degree_keys(const eid_t *__restrict__ off, int64_t n, uint64_t *__restrict__ keys) {
+    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x)
+        keys[v] = ((uint64_t)(off[v + 1] - off[v]) << 32) | (uint32_t)v;
+}
+
+__global__ void k_order_rank(const uint64_t *__restrict__ sorted, int64_t n, vid_t *__restrict__ order,
+                             vid_t *__restrict__ rank) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        vid_t v = (vid_t)(uint32_t)sorted[i];
+        order[i] = v;
+        rank[v] = (vid_t)i;
+    }
+}
+
+// One warp per vertex: d+(u) = |{ v in N(u) : rank[v] > rank[u] }|, stored at cnt[rank[u] + 1].
+__global__ void k_count_out(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, int64_t n,
+                            const vid_t *__restrict__ rank, eid_t *__restrict__ cnt) {
+    int lane = threadIdx.x & 31;
+    int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t u = warp; u < n; u += nwarps) {
+        eid_t b = off[u], e = off[u + 1];
+        vid_t ru = rank[u];
+        int c = 0;
+        for (eid_t s = b + lane; s < e; s += 32) c += rank[nbr[s]] > ru;
+        for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (lane == 0) cnt[ru + 1] = c;
+    }
+}
+
+// One warp per vertex: write (rank[u]<<32 | rank[v]) for the kept slots, compacted with ballots, into the
+// segment of rank[u]; the order inside a segment is fixed afterwards by the radix sort.
+__global__ void k_emit_out(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, int64_t n,
+                           const vid_t *__restrict__ rank, const eid_t *__restrict__ doff,
+                           uint64_t *__restrict__ keys) {
+    int lane = threadIdx.x & 31;
+    int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t u = warp; u < n; u += nwarps) {
+        eid_t b = off[u], e = off[u + 1];
+        vid_t ru = rank[u];
+        eid_t w = doff[ru];
+        uint64_t hi = (uint64_t)(uint32_t)ru << 32;
+        for (eid_t s0 = b; s0 < e; s0 += 32) {
+            eid_t s = s0 + lane;
+            vid_t rv = s < e ? rank[nbr[s]] : -1;
+            bool kp = rv > ru;
+            unsigned mask = __ballot_sync(0xffffffffu, kp);
+            if (kp) keys[w + __popc(mask & ((1u << lane) - 1))] = hi | (uint32_t)rv;
+            w += __popc(mask);
+        }
+    }
+}
+
+__global__ void k_low32(const uint64_t *__restrict__ keys, int64_t K, vid_t *__restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < K; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (vid_t)(uint32_t)keys[i];
+}
+
+__global__ void k_max_deg(const eid_t *__restrict__ off, int64_t n, int *out) {
+    int mx = 0;
+    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x)
+        mx = max(mx, (int)(off[v + 1] - off[v]));
+    for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, mx);
+}
+
+// last vertex with a non-empty list, +1 (InduceDirectedGraph's n = max id seen in the edge list + 1)
+__global__ void k_max_endpoint(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, int64_t n, int *out) {
+    int mx = 0;
+    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x) {
+        eid_t b = off[v], e = off[v + 1];
+        if (e > b) mx = max(mx, max((int)v, (int)nbr[e - 1]));
+    }
+    for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, mx);
+}
+
+__global__ void k_check_perm(const vid_t *__restrict__ rank, int64_t n, int *__restrict__ seen, int *bad) {
+    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x) {
+        vid_t r = rank[v];
+        if (r < 0 || r >= n || atomicExch(&seen[r], 1)) *bad = 1;
+    }
+}
+
+}  // namespace
+
+void degree_order(const Graph &g, DevBuf<vid_t> &order, DevBuf<vid_t> &rank) {
+    Runtime &r = rt();
+    int64_t n = g.n;
+    order.alloc(n);
+    rank.alloc(n);
+    if (n == 0) return;
+    DevBuf<uint64_t> keys(n), alt(n);
+    k_degree_keys<<<grid_for(n, 256), 256, 0, r.stream>>>(g.off.p, n, keys.p); launched();
+    uint64_t *sorted = radix_sort_keys(keys.p, alt.p, n, 0, 64);     // (degree asc, id asc)
+    k_order_rank<<<grid_for(n, 256), 256, 0, r.stream>>>(sorted, n, order.p, rank.p); launched();
+}
+
+void orient_by_rank(const Graph &g, const vid_t *rank_dev, DevBuf<eid_t> &doff, DevBuf<vid_t> &dnbr, int64_t *m_out,
+                    int *max_dplus) {
+    Runtime &r = rt();
+    int64_t n = g.n;
+    doff.alloc(n + 1);
+    doff.zero();
+    if (n) {
+        k_count_out<<<grid_for(n * 32, 256), 256, 0, r.stream>>>(g.off.p, g.nbr.p, n, rank_dev, doff.p); launched();
+        inclusive_sum_inplace(doff.p, n + 1);
+    }
+    int64_t m = n ? doff.get(n) : 0;
+    *m_out = m;
+    dnbr.alloc(m);
+    if (m) {
+        DevBuf<uint64_t> keys(m), alt(m);
+        k_emit_out<<<grid_for(n * 32, 256), 256, 0, r.stream>>>(g.off.p, g.nbr.p, n, rank_dev, doff.p, keys.p);
+        launched();
+        uint64_t *sorted = radix_sort_keys(keys.p, alt.p, m, 0, 32 + bits_for((uint64_t)(n - 1)));
+        k_low32<<<grid_for(m, 256), 256, 0, r.stream>>>(sorted, m, dnbr.p); launched();
+    }
+    if (max_dplus) {
+        DevBuf<int> mx(1);
+        mx.zero();
+        if (n) { k_max_deg<<<grid_for(n, 256), 256, 0, r.stream>>>(doff.p, n, mx.p); launched(); }
+        *max_dplus = mx.get(0);
+    }
+}
+
+Dag *build_degree_dag(const Graph &g) {
+    GMSB_REQUIRE(!g.directed, "degree orientation needs an undirected graph");
+    auto *d = new Dag();
+    try {
+        d->n = g.n;
+        degree_order(g, d->order, d->rank);
+        orient_by_rank(g, d->rank.p, d->off, d->nbr, &d->m, &d->max_dplus);
+    } catch (...) { delete d; throw; }
+    return d;
+}
+
+// InduceDirectedGraph: the result is itself a (directed) Graph handle whose ids are ranks.
+Graph *induce_directed(const Graph &g, const vid_t *ranking_host) {
+    GMSB_REQUIRE(!g.directed, "Graph must be undirected");          // apply_order.h:14-16
+    GMSB_REQUIRE(ranking_host != nullptr || g.n == 0, "orient: null ranking");
+    Runtime &r = rt();
+    int64_t n = g.n;
+    DevBuf<vid_t> rank(n);
+    rank.upload(ranking_host, n);
+    if (n) {
+        DevBuf<int> seen(n + 1);
+        seen.zero();
+        k_check_perm<<<grid_for(n, 256), 256, 0, r.stream>>>(rank.p, n, seen.p, seen.p + n); launched();
+        GMSB_REQUIRE(seen.get(n) == 0, "orient: ranking is not a permutation of 0..n-1");
+    }
+    auto *out = new Graph();
+    try {
+        out->directed = true;
+        int64_t m = 0;
+        orient_by_rank(g, rank.p, out->off, out->nbr, &m, nullptr);
+        out->slots = m;
+        // n = max id that occurs in the induced edge list + 1 (builder.h:285); an empty list gives n = 1
+        DevBuf<int> mx(1);
+        mx.zero();
+        if (n) { k_max_endpoint<<<grid_for(n, 256), 256, 0, r.stream>>>(out->off.p, out->nbr.p, n, mx.p); launched(); }
+        out->n = (int64_t)mx.get(0) + 1;
+        GMSB_CUDA(cudaStreamSynchronize(r.stream));
+    } catch (...) { delete out; throw; }
+    return out;
+}
+
+Dag::~Dag() { delete_plan(plan); }
+Graph::~Graph() { delete dag; }
+
+}  // namespace gmsb

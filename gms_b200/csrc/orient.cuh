@@ -1,0 +1,37 @@
+// orient.cuh — the rank-space oriented DAG and the entry points that build it.
+#pragma once
+#include "common.cuh"
+
+namespace gmsb {
+
+struct TcPlan;
+void delete_plan(TcPlan *p);     // tc.cu
+
+// Degree-oriented DAG of an undirected graph, in rank space (vertex id == position in (degree asc, id asc)).
+struct Dag {
+    int64_t n = 0;
+    int64_t m = 0;               // oriented edges
+    int max_dplus = 0;
+    DevBuf<vid_t> order;         // rank -> original id
+    DevBuf<vid_t> rank;          // original id -> rank
+    DevBuf<eid_t> off;           // n+1
+    DevBuf<vid_t> nbr;           // m, ascending within each list, all entries > owner
+    TcPlan *plan = nullptr;      // cached schedule for the triangle kernels
+    ~Dag();
+};
+
+void degree_order(const Graph &g, DevBuf<vid_t> &order, DevBuf<vid_t> &rank);
+void orient_by_rank(const Graph &g, const vid_t *rank_dev, DevBuf<eid_t> &doff, DevBuf<vid_t> &dnbr, int64_t *m_out,
+                    int *max_dplus);
+Dag *build_degree_dag(const Graph &g);
+Graph *induce_directed(const Graph &g, const vid_t *ranking_host);
+
+// graph_build.cu
+Graph *graph_from_csr_device(int64_t n, const eid_t *off, const vid_t *nbr, bool directed, bool host_src);
+Graph *graph_from_edgelist_device(int64_t m, const vid_t *src, const vid_t *dst, bool symmetrize);
+Graph *graph_relabel_by_degree(const Graph &in);
+
+// tc.cu
+void tc_total(Graph &g, const gmsb_tc_options &opt, uint64_t *out, gmsb_tc_stats *stats);
+
+}  // namespace gmsb

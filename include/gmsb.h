@@ -1,0 +1,171 @@
+/*
+ * gmsb.h — C ABI of gms-b200: the B200-native replacement for GraphMineSuite's set-intersection hot path.
+ *
+ * GMS (spcl/gms) is header-only C++ and has no ABI of its own; the entry points below are what a
+ * binding for this path has to reach, one per reference interface that is replaced.  Citations are
+ * file:line relative to the reference tree.  The C++ facade in include/gms_b200/ wraps these in GMS-named
+ * templates (CudaSetGraph, GMS::TriangleCount::Par::count_total, ...); INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative gmsb_status; gmsb_last_error() gives the message of the
+ *     last failure on the calling thread;
+ *   - handles are opaque; all array arguments are HOST pointers owned by the caller unless the name ends in
+ *     `_device` (then they are device pointers on the current device);
+ *   - vertex ids are int32 (gms/common/types.h:9), offsets int64, counts uint64 / int64 as in the reference;
+ *   - one host thread per handle at a time; the library works on one CUDA device per process
+ *     (gmsb_set_device) and launches on the stream given by gmsb_set_stream (default: the legacy stream 0);
+ *   - there is NO CPU fallback: without a usable CUDA device every compute entry point fails with
+ *     GMSB_ERR_CUDA.
+ */
+#ifndef GMSB_H_
+#define GMSB_H_
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define GMSB_API __attribute__((visibility("default")))
+#else
+#define GMSB_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gmsb_graph_s *gmsb_graph_t;
+
+typedef enum {
+    GMSB_OK = 0,
+    GMSB_ERR_INVALID = -1,   /* bad argument (null pointer, negative size, directed graph where undirected needed) */
+    GMSB_ERR_CUDA = -2,      /* CUDA runtime failure, incl. "no device" */
+    GMSB_ERR_OOM = -3,
+    GMSB_ERR_UNSUPPORTED = -4
+} gmsb_status;
+
+/* ---- runtime -------------------------------------------------------------------------------------------- */
+GMSB_API const char *gmsb_last_error(void);
+GMSB_API int gmsb_version(void);
+GMSB_API int gmsb_device_count(int *count);
+GMSB_API int gmsb_set_device(int device);
+GMSB_API int gmsb_set_stream(void *cuda_stream);            /* cudaStream_t; NULL = legacy default stream */
+GMSB_API int gmsb_synchronize(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+GMSB_API int gmsb_launch_count(uint64_t *count);
+
+/* ---- synthetic inputs (host side; input preparation, never timed) ---------------------------------------------- */
+/* Generator::MakeRMatEL + PermuteIDs                    gms/third_party/gapbs/generator.h:81-114,52-62
+ * m edges of a 2^scale-vertex R-MAT graph, mt19937 reseeded with 27491095 + block every 2^18 edges; the reference's
+ * "kronecker" is a=.57 b=.19 c=.19 with permute=1. Bit-identical to the reference for those constants. */
+GMSB_API int gmsb_generate_rmat(int scale, int64_t m, float a, float b, float c, int permute, int32_t *src,
+                                int32_t *dst);
+/* Generator::MakeUniformEL                              gms/third_party/gapbs/generator.h:64-79 */
+GMSB_API int gmsb_generate_uniform(int scale, int64_t m, int32_t *src, int32_t *dst);
+
+/* ---- graph construction (replaces gapbs CSRGraph / Builder + SetGraph::FromCGraph) ---------------------------- */
+/* SetGraph<Set>::FromCGraph(const CSRGraph&)            gms/representations/graphs/set_graph.h:87-89,153-181
+ * Lists must be ascending and duplicate-free (what SquishGraph leaves, gapbs/builder.h:206-235). */
+GMSB_API int gmsb_graph_from_csr(int64_t n, const int64_t *offsets, const int32_t *nbrs, int directed, gmsb_graph_t *out);
+GMSB_API int gmsb_graph_from_csr_device(int64_t n, const int64_t *offsets, const int32_t *nbrs, int directed,
+                               gmsb_graph_t *out);
+/* BuilderBase::MakeGraphFromEL + SquishGraph            gms/third_party/gapbs/builder.h:279-298,237-251
+ * n = max id + 1; symmetrize inserts both directions; lists sorted, de-duplicated, self loops removed —
+ * done by an on-GPU radix sort of 64-bit (u<<32|v) keys. */
+GMSB_API int gmsb_graph_from_edgelist(int64_t m, const int32_t *src, const int32_t *dst, int symmetrize, gmsb_graph_t *out);
+GMSB_API int gmsb_graph_from_edgelist_device(int64_t m, const int32_t *src, const int32_t *dst, int symmetrize,
+                                    gmsb_graph_t *out);
+/* BuilderBase::RelabelByDegree (degree desc, id desc)   gms/third_party/gapbs/builder.h:1699-1735 */
+GMSB_API int gmsb_graph_relabel_by_degree(gmsb_graph_t g, gmsb_graph_t *out);
+GMSB_API int gmsb_graph_num_nodes(gmsb_graph_t g, int64_t *n);
+GMSB_API int gmsb_graph_num_slots(gmsb_graph_t g, int64_t *slots);     /* CSR entries: 2m undirected, m directed */
+GMSB_API int gmsb_graph_is_directed(gmsb_graph_t g, int *directed);
+GMSB_API int gmsb_graph_export_csr(gmsb_graph_t g, int64_t *offsets, int32_t *nbrs);
+GMSB_API int gmsb_graph_free(gmsb_graph_t g);
+
+/* ---- preprocessing: orderings and orientation ------------------------------------------------------------------- */
+/* PpParallel::getDegreeOrdering<G,useRankFormat>        gms/algorithms/preprocessing/parallel/degree.h:26-61
+ * (degree asc, id asc); rank_format=0: out[i] = vertex at position i; 1: out[v] = position of v. */
+GMSB_API int gmsb_order_degree(gmsb_graph_t g, int rank_format, int32_t *out);
+/* PpSequential::getDegeneracyOrderingDanischHeap        gms/algorithms/preprocessing/sequential/degeneracy_danisch.h:12-56
+ * a valid min-degree-peeling order in the reference's convention rank = n - (removal index); ties are
+ * implementation-defined in the reference too. */
+GMSB_API int gmsb_order_degeneracy(gmsb_graph_t g, int32_t *out_rank);
+/* PpSequential::InduceDirectedGraph(g, ranking)         gms/algorithms/preprocessing/sequential/apply_order.h:10-35
+ * relabels u -> ranking[u], keeps rank(u) < rank(v); result n = max surviving id + 1. Fails with
+ * GMSB_ERR_INVALID on a directed input (the reference throws std::invalid_argument, :14-16). */
+GMSB_API int gmsb_orient(gmsb_graph_t g, const int32_t *ranking, gmsb_graph_t *dag);
+
+/* ---- triangle counting --------------------------------------------------------------------------------------------- */
+/* TriangleCount::{Seq,Par}::count_total                 gms/algorithms/set_based/triangle_count/parallel/total.h:8-24 */
+GMSB_API int gmsb_tc_total(gmsb_graph_t g, uint64_t *out);
+
+/* Which intersection kernel handles an oriented edge (u,v). AUTO picks per edge: the shared-memory bitmap kernel
+ * when v is a hub, else merge-path or galloping by the length ratio of the two lists. */
+typedef enum { GMSB_TC_AUTO = 0, GMSB_TC_MERGE = 1, GMSB_TC_GALLOP = 2, GMSB_TC_BITMAP = 3 } gmsb_tc_variant;
+
+typedef struct {
+    int32_t variant;         /* gmsb_tc_variant */
+    int32_t part_index;      /* this process handles share part_index of part_count of the oriented edges   */
+    int32_t part_count;      /* (multi-GPU: edge partition balanced by work, CSR replicated); 0 or 1 = all    */
+    int32_t reuse_plan;      /* 1: keep the oriented DAG + schedule cached on the handle between calls        */
+    int32_t hub_bitmap_bits; /* bitmap kernel's shared-memory window in bits; 0 = default                     */
+    int32_t gallop_ratio;    /* galloping when longer/shorter >= ratio; 0 = default                           */
+    int64_t hub_min_work;    /* a vertex is a hub when its incoming wedge work >= this; 0 = default            */
+    int32_t reserved[4];
+} gmsb_tc_options;
+
+typedef struct {
+    uint64_t triangles;        /* this part's count (sum over parts = total)                                   */
+    uint64_t algorithmic_bytes;/* B_TC share: sum over this part's oriented edges of 4*(d+(u)+d+(v))            */
+    uint64_t wedges_checked;   /* list elements actually probed                                                */
+    int64_t oriented_edges;    /* |E+| of the whole graph                                                       */
+    int64_t edges_bitmap, edges_merge, edges_gallop;   /* this part's edges by kernel                          */
+    double ms_orient;          /* device ms: degree ranking + DAG build + schedule                              */
+    double ms_count;           /* device ms: all counting kernels                                               */
+    double ms_bitmap, ms_merge, ms_gallop;             /* per-kernel device ms (launched back to back)          */
+    int32_t launches;          /* kernels launched by this call                                                 */
+    int32_t max_dplus;
+    uint64_t bytes_bitmap;     /* algorithmic bytes of the edges the bitmap kernel handles (whole graph)        */
+    uint64_t bytes_light;      /* ... of the edges the merge + gallop kernels handle                            */
+    uint64_t wedges_bitmap;    /* list elements the bitmap kernel probes (whole graph)                          */
+    int64_t bitmap_items;      /* CTAs of the bitmap kernel (whole graph)                                       */
+    int32_t bitmap_smem_bytes; /* dynamic shared memory per CTA of the bitmap kernel                            */
+    int32_t reserved;
+} gmsb_tc_stats;
+
+GMSB_API int gmsb_tc_total_ex(gmsb_graph_t g, const gmsb_tc_options *opt, uint64_t *out, gmsb_tc_stats *stats);
+
+/* TriangleCount::{Seq,Par}::vertex_count2 (= 2*t(u))    gms/algorithms/set_based/triangle_count/parallel/vertex.h:15-49 */
+GMSB_API int gmsb_tc_vertex2(gmsb_graph_t g, int64_t *out_n);
+
+/* ---- batched Set algebra (SortedSet::intersect_count / intersect on neighbourhoods) ----------------------------- */
+/* SortedSetBase::intersect_count                        gms/representations/sets/sorted_set.h:176-182
+ * out[i] = |N(a[i]) ∩ N(b[i])| */
+GMSB_API int gmsb_intersect_count_batch(gmsb_graph_t g, int64_t npairs, const int32_t *a, const int32_t *b, uint64_t *out);
+/* SortedSetBase::intersect                              gms/representations/sets/sorted_set.h:160-166
+ * two-pass: out_offsets[npairs+1] always written; out_elems may be NULL to size the result first. */
+GMSB_API int gmsb_intersect_batch(gmsb_graph_t g, int64_t npairs, const int32_t *a, const int32_t *b, int64_t *out_offsets,
+                         int32_t *out_elems, int64_t out_capacity);
+
+/* ---- vertex similarity ------------------------------------------------------------------------------------------------ */
+/* GMS::VertexSim::Metric                                gms/algorithms/set_based/vertex_similarity/vertex_similarity.h:18 */
+typedef enum {
+    GMSB_SIM_JACCARD = 0, GMSB_SIM_OVERLAP = 1, GMSB_SIM_ADAMIC_ADAR = 2, GMSB_SIM_RESOURCE = 3,
+    GMSB_SIM_COMM_NEIGH = 4, GMSB_SIM_TOTAL_NEIGH = 5, GMSB_SIM_PREF_ATT = 6
+} gmsb_sim_metric;
+/* vertex_similarity<Metric>(a, b, g) for a batch of pairs   vertex_similarity.h:202-221 */
+GMSB_API int gmsb_pair_similarity(gmsb_graph_t g, int metric, int64_t npairs, const int32_t *a, const int32_t *b, double *out);
+/* one score per undirected edge u<v in CSR order (BASELINE.json configs[3]); returns the edge count in *m_out */
+GMSB_API int gmsb_edge_similarity(gmsb_graph_t g, int metric, double *out, int64_t *m_out);
+
+/* ---- k-cliques ------------------------------------------------------------------------------------------------------------ */
+/* KClique::Par::{NP,EP}_kclisting on an oriented DAG      gms/algorithms/non_set_based/k_clique_list/clique_counting.h:14-34
+ * g may be a DAG from gmsb_orient, or an undirected graph (then it is degree-oriented internally; the count is
+ * orientation-invariant). k==1 -> nodes, k==2 -> edges as parallelize.h:43-44. */
+GMSB_API int gmsb_kclique_count(gmsb_graph_t g, int k, uint64_t *out);
+/* CliqueCount<Set,SGraph,Set2> (returns k!*C_k)           gms/algorithms/set_based/k_clique_count/k_clique_count_set_based.h:20-31 */
+GMSB_API int gmsb_kclique_count_ordered(gmsb_graph_t g, int k, uint64_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GMSB_H_ */

@@ -119,7 +119,11 @@ void uniform_edges(int scale, int64_t m, vid *src, vid *dst) {
         for (int64_t blk = 0; blk < m; blk += kGenBlock) {
             rng.seed(kSeed + blk / kGenBlock);
             int64_t hi = std::min(blk + kGenBlock, m);
-            for (int64_t e = blk; e < hi; ++e) { src[e] = pick(rng); dst[e] = pick(rng); }
+            for (int64_t e = blk; e < hi; ++e) {
+                // Edge(udist(rng), udist(rng)): g++ evaluates constructor arguments right to left, so the FIRST
+                // draw is the destination (generator.h:74)
+                dst[e] = pick(rng); src[e] = pick(rng);
+            }
         }
     }
 }
