@@ -62,7 +62,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "250", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -189,19 +189,24 @@ def run_ours(args):
         c, st = g.tc_total_ex(reuse_plan=True, **opts)
         return c, st
 
+    sampler = ClockSampler(local)
+    if rank == 0 and not args.no_clocks:
+        sampler.start()          # nvidia-smi's own start-up stalls the driver for a moment: keep it out of the timing
+        time.sleep(1.5)
     for _ in range(args.warmup):
         step()
-    sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.rows.clear()     # keep only samples taken under load
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = G.launch_count()
     gd.barrier()
     torch.cuda.synchronize()
     ev0.record()
-    ms_bitmap, ms_count, parts = [], [], []
+    ms_bitmap, ms_count, parts, wall = [], [], [], []
     for _ in range(args.steps):
+        tw = time.perf_counter()
         c, st = step()
+        wall.append((time.perf_counter() - tw) * 1e3)
         parts.append(c)
         ms_bitmap.append(st["ms_bitmap"])
         ms_count.append(st["ms_count"])
@@ -266,7 +271,7 @@ def run_ours(args):
                    "variant": args.variant, "parallelism": f"edge-partition x{world}, CSR replicated",
                    "l2": "inputs_exceed_L2 (oriented CSR %.2f GB vs 126 MB L2)" % (st["oriented_edges"] * 4 / 1e9),
                    "step": "count_total over the prepared device graph; representation build in prep_ms and e2e"},
-        "triangles": expect, "prep_ms": prep_ms, "count_ms": count_ms,
+        "triangles": expect, "prep_ms": prep_ms, "count_ms": count_ms, "step_wall_ms": [round(w, 2) for w in wall],
         "kernel_ms": {"bitmap": bm_ms, "merge": st["ms_merge"], "gallop": st["ms_gallop"]},
         "edges_by_kernel": {"bitmap": st["edges_bitmap"], "merge": st["edges_merge"], "gallop": st["edges_gallop"]},
         "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches),
@@ -306,6 +311,7 @@ def main():
     ap.add_argument("--scale", type=int, default=24)
     ap.add_argument("--variant", default="auto", choices=["auto", "merge", "gallop", "bitmap"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-clocks", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -35,6 +35,10 @@ Runtime &rt() {
             g_rt.device = g_device;
             g_rt.sm_count = prop.multiProcessorCount;
             g_rt.smem_optin = prop.sharedMemPerBlockOptin;
+            cudaMemPool_t pool;
+            GMSB_CUDA(cudaDeviceGetDefaultMemPool(&pool, g_device));
+            uint64_t keep = UINT64_MAX;
+            GMSB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
             g_rt_ready = true;
         }
     }
@@ -97,7 +101,12 @@ GMSB_API int gmsb_set_device(int device) {
     });
 }
 
-GMSB_API int gmsb_set_stream(void *s) { return guarded([&] { rt().stream = reinterpret_cast<cudaStream_t>(s); }); }
+GMSB_API int gmsb_set_stream(void *s) {
+    return guarded([&] {
+        GMSB_CUDA(cudaStreamSynchronize(rt().stream));     // pool memory freed on the old stream must be quiescent
+        rt().stream = reinterpret_cast<cudaStream_t>(s);
+    });
+}
 GMSB_API int gmsb_synchronize(void) { return guarded([&] { GMSB_CUDA(cudaStreamSynchronize(rt().stream)); }); }
 GMSB_API int gmsb_launch_count(uint64_t *count) {
     return guarded([&] { GMSB_REQUIRE(count, "null argument"); *count = g_rt_ready ? g_rt.launches : 0; });

@@ -65,13 +65,16 @@ struct DevBuf {
         return *this;
     }
     ~DevBuf() { release(); }
+    // Stream-ordered allocation from the device's default memory pool, whose release threshold rt() raises to
+    // "never": the multi-GB scratch of a graph build is recycled by the next build instead of being unmapped and
+    // re-mapped by the driver (cudaMalloc/cudaFree of GBs costs more than the kernels they feed).
     void alloc(size_t count) {
         release();
         n = count;
-        if (count) GMSB_CUDA(cudaMalloc(&p, count * sizeof(T)));
+        if (count) GMSB_CUDA(cudaMallocAsync(&p, count * sizeof(T), rt().stream));
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p) cudaFreeAsync(p, rt().stream);
         p = nullptr; n = 0;
     }
     void zero() { if (n) GMSB_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), rt().stream)); }

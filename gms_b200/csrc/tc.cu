@@ -133,7 +133,7 @@ __global__ void k_classify(const eid_t *__restrict__ off, const vid_t *__restric
                        (pp.variant == GMSB_TC_BITMAP || (long long)work[v] >= pp.hub_min_work);
             if (hub) {
                 int64_t words = (span + 31) >> 5;
-                long long setup = 8ll * (words + (oe - ob));
+                long long setup = 16ll * (oe - ob);
                 long long target = pp.item_cost > setup ? pp.item_cost : setup;
                 long long cost = (long long)work[v] + 4ll * cnt;
                 k = (cost + target - 1) / target;
@@ -194,52 +194,75 @@ __global__ void k_compact_light(const uint32_t *__restrict__ keys, const uint64_
 }
 
 // ---- counting kernels ----------------------------------------------------------------------------------------------
-// Hub bitmap kernel: one CTA per item (v, slice of v's incoming suffix descriptors).
-template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK)
-k_tc_bitmap(const Item *__restrict__ items, int64_t first, int64_t stride, const eid_t *__restrict__ off,
-            const vid_t *__restrict__ nbr, const uint64_t *__restrict__ desc, unsigned long long *__restrict__ total) {
-    extern __shared__ uint32_t bm[];
-    __shared__ unsigned long long red[BLOCK / 32];
-    const Item item = items[first + (int64_t)blockIdx.x * stride];
-    const int tid = threadIdx.x;
-    const vid_t v = item.v;
-    const eid_t ob = off[v], oe = off[v + 1];
-    const uint32_t base = (uint32_t)v + 1u;
-    const uint32_t span = (uint32_t)nbr[oe - 1] - (uint32_t)v;
-    const int words = (int)((span + 31u) >> 5);
-    for (int i = tid; i < words; i += BLOCK) bm[i] = 0u;
-    __syncthreads();
-    for (eid_t j = ob + tid; j < oe; j += BLOCK) {
-        uint32_t x = (uint32_t)nbr[j] - base;
-        atomicOr(&bm[x >> 5], 1u << (x & 31));
-    }
-    __syncthreads();
+// Hub bitmap kernel.  Persistent CTAs (one wave, grid = SMs x resident CTAs) pull items (v, slice of v's incoming
+// suffix descriptors) from a global ticket, heaviest first.  The shared-memory bitmap is zeroed ONCE per CTA; each
+// item sets the bits of N+(v), streams its suffixes, then clears exactly the words it set — so the per-item cost
+// is O(d+(v)) and independent of how wide the window (v, last(N+(v))] is.  Inside an item the warps pull
+// descriptors from a shared-memory ticket (suffix lengths vary by 1000x), load list elements with coalesced
+// 4-deep unrolled loads and do ONE branch-free probe per element: out-of-window elements are clamped onto the
+// always-zero guard word bm[cap_words].
+constexpr int kDescChunk = 4;
 
-    const int lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = BLOCK / 32;
-    uint32_t hits = 0;
-    const uint64_t *dptr = desc + item.begin;
-    for (int d = warp; d < item.count; d += NW) {
-        const uint64_t ds = dptr[d];
-        const vid_t *__restrict__ p = nbr + (ds >> kLenBits);
-        const int len = (int)(ds & kLenMask);
-        int j = lane;
-        // 4 independent loads in flight per lane
-        for (; j + 96 < len; j += 128) {
-            uint32_t x0 = (uint32_t)p[j] - base, x1 = (uint32_t)p[j + 32] - base;
-            uint32_t x2 = (uint32_t)p[j + 64] - base, x3 = (uint32_t)p[j + 96] - base;
-            if (x0 < span) hits += (bm[x0 >> 5] >> (x0 & 31)) & 1u;
-            if (x1 < span) hits += (bm[x1 >> 5] >> (x1 & 31)) & 1u;
-            if (x2 < span) hits += (bm[x2 >> 5] >> (x2 & 31)) & 1u;
-            if (x3 < span) hits += (bm[x3 >> 5] >> (x3 & 31)) & 1u;
+__device__ __forceinline__ uint32_t probe(const uint32_t *bm, uint32_t x, uint32_t cap_words) {
+    return (bm[min(x >> 5, cap_words)] >> (x & 31)) & 1u;
+}
+
+template <int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB)
+k_tc_bitmap(const Item *__restrict__ items, int64_t first, int64_t stride, int64_t count, uint32_t cap_words,
+            const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, const uint64_t *__restrict__ desc,
+            unsigned long long *__restrict__ total, unsigned int *__restrict__ ticket) {
+    extern __shared__ uint32_t bm[];                  // cap_words + 1 words
+    __shared__ unsigned long long red[BLOCK / 32];
+    __shared__ unsigned int s_item;
+    __shared__ int s_next;
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (uint32_t i = tid; i <= cap_words; i += BLOCK) bm[i] = 0u;
+    unsigned long long hits64 = 0;
+    for (;;) {
+        if (tid == 0) { s_item = atomicAdd(ticket, 1u); s_next = 0; }
+        __syncthreads();                              // ticket visible; previous item's clears done
+        const int64_t it = (int64_t)s_item;
+        if (it >= count) break;
+        const Item item = items[first + (count - 1 - it) * stride];        // heaviest (highest v) first
+        const vid_t v = item.v;
+        const eid_t ob = off[v], oe = off[v + 1];
+        const uint32_t base = (uint32_t)v + 1u;
+        for (eid_t j = ob + tid; j < oe; j += BLOCK) {
+            const uint32_t x = (uint32_t)nbr[j] - base;
+            atomicOr(&bm[x >> 5], 1u << (x & 31));
         }
-        for (; j < len; j += 32) {
-            uint32_t x = (uint32_t)p[j] - base;
-            if (x < span) hits += (bm[x >> 5] >> (x & 31)) & 1u;
+        __syncthreads();                              // bitmap of N+(v) complete
+
+        uint32_t hits = 0;
+        const uint64_t *__restrict__ dptr = desc + item.begin;
+        const int cnt = item.count;
+        for (;;) {
+            int d0 = 0;
+            if (lane == 0) d0 = atomicAdd(&s_next, kDescChunk);
+            d0 = __shfl_sync(0xffffffffu, d0, 0);
+            if (d0 >= cnt) break;
+            const int nd = min(kDescChunk, cnt - d0);
+            const uint64_t mine = lane < nd ? dptr[d0 + lane] : 0ull;
+            for (int k = 0; k < nd; ++k) {
+                const uint64_t ds = __shfl_sync(0xffffffffu, mine, k);
+                const vid_t *__restrict__ p = nbr + (ds >> kLenBits);
+                const int len = (int)(ds & kLenMask);
+                int j = lane;
+                for (; j + 96 < len; j += 128) {      // 4 independent loads in flight per lane
+                    const uint32_t x0 = (uint32_t)p[j] - base, x1 = (uint32_t)p[j + 32] - base;
+                    const uint32_t x2 = (uint32_t)p[j + 64] - base, x3 = (uint32_t)p[j + 96] - base;
+                    hits += probe(bm, x0, cap_words) + probe(bm, x1, cap_words) + probe(bm, x2, cap_words) +
+                            probe(bm, x3, cap_words);
+                }
+                for (; j < len; j += 32) hits += probe(bm, (uint32_t)p[j] - base, cap_words);
+            }
         }
+        hits64 += hits;
+        __syncthreads();                              // every probe of this item done
+        for (eid_t j = ob + tid; j < oe; j += BLOCK) bm[((uint32_t)nbr[j] - base) >> 5] = 0u;
     }
-    unsigned long long s = block_sum(hits, red);
+    unsigned long long s = block_sum(hits64, red);
     if (tid == 0 && s) atomicAdd(total, s);
 }
 
@@ -296,13 +319,13 @@ gmsb_tc_options normalise(const gmsb_tc_options *in) {
     if (o.part_count <= 0) { o.part_count = 1; o.part_index = 0; }
     if (o.hub_bitmap_bits <= 0) o.hub_bitmap_bits = 512 * 1024;      // 64 KB of shared memory
     if (o.gallop_ratio <= 0) o.gallop_ratio = 8;
-    if (o.hub_min_work <= 0) o.hub_min_work = 2048;
+    if (o.hub_min_work <= 0) o.hub_min_work = 4096;
     return o;
 }
 
 bool same_plan(const gmsb_tc_options &a, const gmsb_tc_options &b) {
     return a.variant == b.variant && a.hub_bitmap_bits == b.hub_bitmap_bits && a.gallop_ratio == b.gallop_ratio &&
-           a.hub_min_work == b.hub_min_work;
+           a.hub_min_work == b.hub_min_work && a.reserved[0] == b.reserved[0];
 }
 
 TcPlan *build_plan(const Dag &d, const gmsb_tc_options &opt) {
@@ -339,7 +362,8 @@ TcPlan *build_plan(const Dag &d, const gmsb_tc_options &opt) {
         k_lower_bounds<<<grid_for(n + 1, 256), 256, 0, r.stream>>>(p->sorted_keys, cnt, n, inoff.p); launched();
         DevBuf<int> mxw(1);
         mxw.zero(); nitems.zero();
-        PlanParams pp{opt.variant, hub_bits, (long long)opt.hub_min_work, 32768};
+        PlanParams pp{opt.variant, hub_bits, (long long)opt.hub_min_work,
+                      opt.reserved[0] > 0 ? (long long)opt.reserved[0] : 262144ll};
         k_classify<<<grid_for(n, 256), 256, 0, r.stream>>>(d.off.p, d.nbr.p, n, inoff.p, work.p, vbytes.p, cls.p, pp, nitems.p,
                                                           mxw.p);
         launched();
@@ -418,14 +442,21 @@ void tc_total(Graph &g, const gmsb_tc_options &opt_in, uint64_t *out, gmsb_tc_st
 
     t_bm.start();
     if (my_items) {
-        constexpr int BLOCK = 512;
-        size_t smem = (size_t)p.max_span_words * 4;
+        constexpr int BLOCK = 512, MINB = 3;
+        auto kern = k_tc_bitmap<BLOCK, MINB>;
+        const size_t smem = ((size_t)p.max_span_words + 1) * 4;
         if (smem > 48 * 1024)
-            GMSB_CUDA(cudaFuncSetAttribute(k_tc_bitmap<BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            GMSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int resident = 0;
+        GMSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, BLOCK, smem));
+        GMSB_REQUIRE(resident >= 1, "tc: bitmap kernel does not fit on an SM");
         GMSB_REQUIRE(my_items < (int64_t(1) << 31), "tc: too many bitmap items");
-        k_tc_bitmap<BLOCK><<<(unsigned)my_items, BLOCK, smem, r.stream>>>(p.items.p, pi, P, d.off.p, d.nbr.p,
-                                                                        p.sorted_vals, total.p);
-        launched();
+        const int grid = (int)std::min<int64_t>(my_items, (int64_t)r.sm_count * resident);   // one persistent wave
+        DevBuf<unsigned int> ticket(1);
+        ticket.zero();
+        kern<<<grid, BLOCK, smem, r.stream>>>(p.items.p, pi, P, my_items, (uint32_t)p.max_span_words, d.off.p, d.nbr.p,
+                                              p.sorted_vals, total.p, ticket.p);
+        launched();                                        // (ticket's free is stream-ordered after the kernel)
     }
     t_bm.stop();
     t_mg.start();
