@@ -249,9 +249,10 @@ class Graph:
         return out.value
 
     def tc_total_ex(self, variant="auto", part_index=0, part_count=1, reuse_plan=False, hub_bitmap_bits=0,
-                    gallop_ratio=0, hub_min_work=0):
+                    gallop_ratio=0, hub_min_work=0, item_cost=0, tile_shift=0, cta_shape=0):
+        """item_cost / tile_shift / cta_shape are tuning knobs carried in gmsb_tc_options.reserved[0..2]."""
         opt = TcOptions(TC_VARIANTS[variant], part_index, part_count, int(reuse_plan), hub_bitmap_bits, gallop_ratio,
-                        hub_min_work)
+                        hub_min_work, (C.c_int32 * 4)(item_cost, tile_shift, cta_shape, 0))
         out, st = C.c_uint64(0), TcStats()
         _check(lib().gmsb_tc_total_ex(self.h, C.byref(opt), C.byref(out), C.byref(st)))
         return out.value, st.as_dict()

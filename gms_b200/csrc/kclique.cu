@@ -1,0 +1,376 @@
+// kclique.cu — k-clique counting on an oriented DAG.
+//
+// Replaces:
+//   KClique::KcListing / Parallelize::{node,edge}     gms/algorithms/non_set_based/k_clique_list/kernels/kclisting.h:19-189,
+//                                                     parallelizationStrategy/parallelize.h:39-121
+//   Builders::SubGraphBuilder::buildSubGraph          parallelizationStrategy/SubGraphBuilder.h:42-123
+//   CliqueCount<Set,SGraph,Set2> (k! * C_k)           gms/algorithms/set_based/k_clique_count/k_clique_count_set_based.h:6-31
+//
+// The reference builds, per vertex or per edge, an induced sub-DAG as a fresh CSR (new NodeId[c*c]) and walks it
+// with label arrays, counting the last level one clique at a time.  Here the induced sub-DAG on S = N+(u) is a
+// |S| x |S| BIT MATRIX held on chip (row i = members of S that are out-neighbours of S[i]); a recursion level is one
+// AND of a candidate bitset with a row, and the last level is a popcount, so the cost is proportional to the number
+// of (k-1)-cliques rather than k-cliques and no memory is allocated per sub-problem.
+//   d+(u) <= 32 : one warp per u, the matrix lives in 32 registers' worth of shared words, every lane runs the
+//                 depth-first search of one first-level member with single 32-bit masks;
+//   d+(u)  > 32 : one CTA per u, matrix in shared memory (rows built by streaming N+(S[i]) and binary-searching S),
+//                 warps pull first-level members from a ticket and search with lane-distributed bitsets.
+// Every acyclic orientation counts each clique exactly once, so the result equals the reference's for any
+// ranking (degree, degeneracy, ...).
+#include "common.cuh"
+#include "sort.cuh"
+#include "isect.cuh"
+#include "orient.cuh"
+#include "ops.cuh"
+
+namespace gmsb {
+
+namespace {
+
+constexpr int kMaxK = 16;
+constexpr int kBigBlock = 512;
+
+// ---- d+(u) <= 32 -----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long dfs32(const uint32_t *rows, uint32_t cand, int need) {
+    // number of `need`-cliques inside `cand` (bit i = member i), rows[i] = out-neighbours of member i inside S
+    if (need == 1) return __popc(cand);
+    unsigned long long total = 0;
+    uint32_t it[kMaxK], cur[kMaxK];
+    int level = 0;
+    cur[0] = cand; it[0] = cand;
+    for (;;) {
+        if (it[level] == 0) {
+            if (level == 0) break;
+            --level;
+            continue;
+        }
+        const int i = __ffs(it[level]) - 1;
+        it[level] &= it[level] - 1;
+        const uint32_t nxt = cur[level] & rows[i];
+        const int left = need - level - 1;          // vertices still to pick after choosing i
+        if (left == 1) total += __popc(nxt);
+        else if (__popc(nxt) >= left) { ++level; cur[level] = nxt; it[level] = nxt; }
+    }
+    return total;
+}
+
+__global__ void __launch_bounds__(256)
+k_kclique_small(const vid_t *__restrict__ verts, int64_t count, const eid_t *__restrict__ off,
+                const vid_t *__restrict__ nbr, int k, unsigned long long *__restrict__ total) {
+    __shared__ uint32_t rows_s[8][32];
+    __shared__ unsigned long long red[8];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    uint32_t *rows = rows_s[wib];
+    unsigned long long acc = 0;
+    for (int64_t t = warp; t < count; t += nwarps) {
+        const vid_t u = verts[t];
+        const eid_t ob = off[u];
+        const int D = (int)(off[u + 1] - ob);                 // <= 32
+        const vid_t mine = lane < D ? nbr[ob + lane] : -1;    // member `lane` of S
+        // row of member `lane`: for every later member j, is S[j] in N+(S[lane]) ?
+        uint32_t row = 0;
+        if (lane < D) {
+            const eid_t mb = off[mine];
+            const int md = (int)(off[mine + 1] - mb);
+            const vid_t *ml = nbr + mb;
+            for (int j = lane + 1; j < D; ++j) {
+                const vid_t w = nbr[ob + j];
+                const int p = lower_bound_dev(ml, md, w);
+                if (p < md && ml[p] == w) row |= 1u << j;
+            }
+        }
+        __syncwarp();
+        rows[lane] = row;
+        __syncwarp();
+        // member `lane` is the second clique vertex; k-2 more are picked inside its row
+        if (lane < D) acc += k == 2 ? 1ull : dfs32(rows, row, k - 2);
+    }
+    unsigned long long s = block_sum(acc, red);
+    if (threadIdx.x == 0 && s) atomicAdd(total, s);
+}
+
+// ---- d+(u) > 32 --------------------------------------------------------------------------------------------------------
+// Bitsets of W words are spread over the warp: word w lives in lane (w & 31), slot (w >> 5); WPL slots per lane.
+template <int WPL>
+struct WarpSet {
+    uint32_t w[WPL];
+};
+
+template <int WPL>
+__device__ __forceinline__ int first_bit(const WarpSet<WPL> &s, int lane) {
+    // index of the lowest set bit over the whole warp-distributed bitset, or -1
+#pragma unroll
+    for (int slot = 0; slot < WPL; ++slot) {
+        const unsigned m = __ballot_sync(0xffffffffu, s.w[slot] != 0);
+        if (m) {
+            const int L = __ffs(m) - 1;
+            const uint32_t word = __shfl_sync(0xffffffffu, s.w[slot], L);
+            return ((slot << 5) + L) * 32 + (__ffs(word) - 1);
+        }
+    }
+    return -1;
+}
+
+template <int WPL>
+__device__ unsigned long long dfs_warp(const uint32_t *rows, int W, WarpSet<WPL> cand, int need, int lane) {
+    // per-lane partial count of `need`-cliques inside cand; caller reduces over the warp
+    unsigned long long total = 0;
+    if (need == 1) {
+#pragma unroll
+        for (int s = 0; s < WPL; ++s) total += __popc(cand.w[s]);
+        return total;
+    }
+    WarpSet<WPL> it[kMaxK - 2], cur[kMaxK - 2];
+    int level = 0;
+    cur[0] = cand; it[0] = cand;
+    for (;;) {
+        const int i = first_bit<WPL>(it[level], lane);
+        if (i < 0) {
+            if (level == 0) break;
+            --level;
+            continue;
+        }
+        {   // clear bit i in the iterator
+            const int w = i >> 5;
+            if ((w & 31) == lane) it[level].w[w >> 5] &= ~(1u << (i & 31));
+        }
+        WarpSet<WPL> nxt;
+        int pc = 0;
+#pragma unroll
+        for (int s = 0; s < WPL; ++s) {
+            const int w = lane + (s << 5);
+            nxt.w[s] = w < W ? (cur[level].w[s] & rows[(size_t)i * W + w]) : 0u;
+            pc += __popc(nxt.w[s]);
+        }
+        const int left = need - level - 1;
+        if (left == 1) total += pc;
+        else {
+            // descend only if enough candidates remain (warp-wide popcount)
+            int all = pc;
+            for (int o = 16; o; o >>= 1) all += __shfl_xor_sync(0xffffffffu, all, o);
+            if (all >= left) { ++level; cur[level] = nxt; it[level] = nxt; }
+        }
+    }
+    return total;
+}
+
+template <int WPL>
+__global__ void __launch_bounds__(kBigBlock)
+k_kclique_big(const vid_t *__restrict__ verts, int64_t count, const eid_t *__restrict__ off,
+              const vid_t *__restrict__ nbr, int k, int maxD, unsigned long long *__restrict__ total,
+              unsigned int *__restrict__ ticket, uint32_t *__restrict__ spill) {
+    extern __shared__ uint32_t smem[];
+    // member list + bit matrix live in shared memory, or — when max d+ makes them larger than an SM's shared
+    // memory — in this CTA's slice of a global scratch buffer (L2-resident for the sizes that occur)
+    uint32_t *store = spill ? spill + (size_t)blockIdx.x * ((size_t)maxD + (size_t)maxD * ((maxD + 31) >> 5)) : smem;
+    vid_t *S = reinterpret_cast<vid_t *>(store);           // maxD members
+    uint32_t *rows = store + maxD;                         // D x W bit matrix
+    __shared__ unsigned long long red[kBigBlock / 32];
+    __shared__ unsigned int s_item;
+    __shared__ int s_next;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = kBigBlock / 32;
+    unsigned long long acc = 0;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) { s_item = atomicAdd(ticket, 1u); s_next = 0; }
+        __syncthreads();
+        const int64_t t = (int64_t)s_item;
+        if (t >= count) break;
+        const vid_t u = verts[t];
+        const eid_t ob = off[u];
+        const int D = (int)(off[u + 1] - ob);
+        const int W = (D + 31) >> 5;
+        for (int j = tid; j < D; j += kBigBlock) S[j] = nbr[ob + j];
+        for (int j = tid; j < D * W; j += kBigBlock) rows[j] = 0u;
+        __syncthreads();
+        // rows: warp per member i streams N+(S[i]) and looks every element up in S
+        for (int i = warp; i < D; i += NW) {
+            const vid_t vi = S[i];
+            const eid_t mb = off[vi];
+            const int md = (int)(off[vi + 1] - mb);
+            for (int j = lane; j < md; j += 32) {
+                const vid_t w = nbr[mb + j];
+                int lo = i + 1, hi = D;                     // members after i only (ids ascend with position)
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (S[mid] < w) lo = mid + 1; else hi = mid;
+                }
+                if (lo < D && S[lo] == w) atomicOr(&rows[(size_t)i * W + (lo >> 5)], 1u << (lo & 31));
+            }
+        }
+        __syncthreads();
+        // search: a warp takes first-level member i; its row is the candidate set for the other k-2 vertices
+        for (;;) {
+            int i = 0;
+            if (lane == 0) i = atomicAdd(&s_next, 1);
+            i = __shfl_sync(0xffffffffu, i, 0);
+            if (i >= D) break;
+            WarpSet<WPL> cand;
+#pragma unroll
+            for (int s = 0; s < WPL; ++s) {
+                const int w = lane + (s << 5);
+                cand.w[s] = w < W ? rows[(size_t)i * W + w] : 0u;
+            }
+            acc += dfs_warp<WPL>(rows, W, cand, k - 2, lane);
+        }
+    }
+    unsigned long long s = block_sum(acc, red);
+    if (tid == 0 && s) atomicAdd(total, s);
+}
+
+// vertices with enough out-neighbours for a k-clique, split by d+ <= 32
+__global__ void k_bucket_flags(const eid_t *__restrict__ off, int64_t n, int k, uint8_t *__restrict__ small,
+                               uint8_t *__restrict__ big, int *__restrict__ maxd) {
+    int mx = 0;
+    for (int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; u < n; u += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t d = off[u + 1] - off[u];
+        const bool ok = d >= k - 1;
+        small[u] = ok && d <= 32;
+        big[u] = ok && d > 32;
+        if (ok && d > 32) mx = max(mx, (int)d);
+    }
+    for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0 && mx) atomicMax(maxd, mx);
+}
+__global__ void k_bucket_fill(int64_t n, const uint8_t *__restrict__ flag, const int64_t *__restrict__ pos,
+                              vid_t *__restrict__ out) {
+    for (int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; u < n; u += (int64_t)gridDim.x * blockDim.x)
+        if (flag[u]) out[pos[u]] = (vid_t)u;
+}
+
+// big vertices sorted by descending out-degree so that the heaviest sub-problems start first
+__global__ void k_degree_key(const vid_t *__restrict__ verts, int64_t cnt, const eid_t *__restrict__ off,
+                             uint64_t *__restrict__ keys) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < cnt; i += (int64_t)gridDim.x * blockDim.x) {
+        const vid_t u = verts[i];
+        keys[i] = ((uint64_t)(off[u + 1] - off[u]) << 32) | (uint32_t)u;
+    }
+}
+__global__ void k_key_vertex(const uint64_t *__restrict__ keys, int64_t cnt, vid_t *__restrict__ verts) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < cnt; i += (int64_t)gridDim.x * blockDim.x)
+        verts[i] = (vid_t)(uint32_t)keys[i];
+}
+
+uint64_t count_on_dag(int64_t n, int64_t m, const eid_t *off, const vid_t *nbr, int k) {
+    Runtime &r = rt();
+    if (k == 1) return (uint64_t)n;                // parallelize.h:43
+    if (k == 2) return (uint64_t)m;                // parallelize.h:44
+    GMSB_REQUIRE(k <= kMaxK, "kclique_count: clique size above 16 is not supported");
+    if (n == 0 || m == 0) return 0;
+    DevBuf<uint8_t> fs(n), fb(n);
+    DevBuf<int64_t> ps(n + 1), pb(n + 1);
+    DevBuf<int> maxd(1);
+    maxd.zero();
+    k_bucket_flags<<<grid_for(n, 256), 256, 0, r.stream>>>(off, n, k, fs.p, fb.p, maxd.p); launched();
+    exclusive_sum(fs.p, ps.p, n);
+    exclusive_sum(fb.p, pb.p, n);
+    const int64_t ns = ps.get(n - 1) + fs.get(n - 1), nb = pb.get(n - 1) + fb.get(n - 1);
+    const int maxD = maxd.get(0);
+    DevBuf<unsigned long long> total(1);
+    total.zero();
+    if (ns) {
+        DevBuf<vid_t> vs(ns);
+        k_bucket_fill<<<grid_for(n, 256), 256, 0, r.stream>>>(n, fs.p, ps.p, vs.p); launched();
+        int grid = (int)std::min<int64_t>(ceil_div(ns, 8), (int64_t)r.sm_count * 16);
+        k_kclique_small<<<grid, 256, 0, r.stream>>>(vs.p, ns, off, nbr, k, total.p); launched();
+    }
+    if (nb) {
+        DevBuf<vid_t> vb(nb);
+        k_bucket_fill<<<grid_for(n, 256), 256, 0, r.stream>>>(n, fb.p, pb.p, vb.p); launched();
+        DevBuf<uint64_t> keys(nb), alt(nb);
+        k_degree_key<<<grid_for(nb, 256), 256, 0, r.stream>>>(vb.p, nb, off, keys.p); launched();
+        uint64_t *sorted = radix_sort_keys(keys.p, alt.p, nb, 0, 64, /*descending=*/true);
+        k_key_vertex<<<grid_for(nb, 256), 256, 0, r.stream>>>(sorted, nb, vb.p); launched();
+        const int W = (maxD + 31) >> 5;
+        if (W > 128)
+            throw Error(GMSB_ERR_UNSUPPORTED, "kclique_count: max out-degree " + std::to_string(maxD) +
+                                                  " exceeds 4096; orient by degree or degeneracy first");
+        const size_t need = ((size_t)maxD + (size_t)maxD * W) * 4;
+        const bool in_smem = need <= r.smem_optin;
+        const size_t smem = in_smem ? need : 0;
+        DevBuf<unsigned int> ticket(1);
+        ticket.zero();
+        DevBuf<uint32_t> spill;
+        auto launch = [&](auto kern) {
+            if (smem > 48 * 1024)
+                GMSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int resident = 0;
+            GMSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, kBigBlock, smem));
+            GMSB_REQUIRE(resident >= 1, "kclique_count: kernel does not fit on an SM");
+            if (!in_smem) resident = 1;
+            const int grid = (int)std::min<int64_t>(nb, (int64_t)r.sm_count * resident);
+            if (!in_smem) spill.alloc((size_t)grid * (need / 4));
+            kern<<<grid, kBigBlock, smem, r.stream>>>(vb.p, nb, off, nbr, k, maxD, total.p, ticket.p,
+                                                      in_smem ? nullptr : spill.p);
+            launched();
+        };
+        if (W <= 32) launch(k_kclique_big<1>);
+        else if (W <= 64) launch(k_kclique_big<2>);
+        else launch(k_kclique_big<4>);
+    }
+    return total.get(0);
+}
+
+}  // namespace
+
+namespace {
+__global__ void k_expand_sources(const eid_t *__restrict__ off, int64_t n, vid_t *__restrict__ src) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t u = warp; u < n; u += nwarps)
+        for (eid_t e = off[u] + lane; e < off[u + 1]; e += 32) src[e] = (vid_t)u;
+}
+__global__ void k_max_out(const eid_t *__restrict__ off, int64_t n, int *out) {
+    int mx = 0;
+    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x)
+        mx = max(mx, (int)(off[v + 1] - off[v]));
+    for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, mx);
+}
+}  // namespace
+
+void kclique_count(Graph &g, int k, uint64_t *out) {
+    if (g.directed) {
+        Runtime &r = rt();
+        if (k <= 2 || g.n == 0 || g.slots == 0) { *out = count_on_dag(g.n, g.slots, g.off.p, g.nbr.p, k); return; }
+        DevBuf<int> mx(1);
+        mx.zero();
+        k_max_out<<<grid_for(g.n, 256), 256, 0, r.stream>>>(g.off.p, g.n, mx.p); launched();
+        const int64_t D = mx.get(0), W = (D + 31) >> 5;
+        if ((size_t)(D + D * W) * 4 <= r.smem_optin) {
+            *out = count_on_dag(g.n, g.slots, g.off.p, g.nbr.p, k);
+            return;
+        }
+        // The reference's own degeneracy pipeline orients from later- to earlier-removed vertices, which leaves
+        // out-degrees unbounded.  Clique counts do not depend on the orientation, so re-orient the
+        // underlying undirected graph by degree and count there.
+        DevBuf<vid_t> src(g.slots);
+        k_expand_sources<<<grid_for(g.n * 32, 256), 256, 0, r.stream>>>(g.off.p, g.n, src.p); launched();
+        Graph *und = graph_from_edgelist_device(g.slots, src.p, g.nbr.p, true);
+        try {
+            und->dag = build_degree_dag(*und);
+            *out = count_on_dag(und->dag->n, und->dag->m, und->dag->off.p, und->dag->nbr.p, k);
+        } catch (...) { delete und; throw; }
+        delete und;
+        return;
+    }
+    if (k == 1) { *out = (uint64_t)g.n; return; }
+    if (!g.dag) g.dag = build_degree_dag(g);
+    *out = count_on_dag(g.dag->n, g.dag->m, g.dag->off.p, g.dag->nbr.p, k);
+}
+
+// CliqueCount on the unoriented graph counts ordered tuples: k! * C_k, with size_t wrap-around.
+void kclique_count_ordered(Graph &g, int k, uint64_t *out) {
+    GMSB_REQUIRE(!g.directed, "kclique_count_ordered: graph must be undirected");
+    uint64_t c = 0;
+    kclique_count(g, k, &c);
+    uint64_t f = 1;
+    for (int i = 2; i <= k; ++i) f *= (uint64_t)i;
+    *out = c * f;
+}
+
+}  // namespace gmsb

@@ -1,0 +1,94 @@
+// kcore.cu — degeneracy ordering by parallel k-core peeling.
+//
+// Replaces  PpSequential::getDegeneracyOrderingDanischHeap   gms/algorithms/preprocessing/sequential/degeneracy_danisch.h:12-56
+//
+// The reference pops one minimum-degree vertex at a time from a heap (O(m log n), sequential) and its tie-breaking
+// is not reproducible (testing/preprocessing.cpp:6-7).  Here all vertices whose residual degree is <= k leave
+// together, their neighbours' degrees drop with atomics, and vertices that fall to <= k join the same level's next
+// frontier.  The result is a valid degeneracy order by the reference's own verifier
+// (verifiers/degeneracy_verifier.h:69-85: every vertex has at most `degeneracy` neighbours that are removed after
+// it), in the reference's ranking convention: the r-th removed vertex (r = 1..n) gets rank n - r.
+#include "common.cuh"
+#include "isect.cuh"
+#include "ops.cuh"
+
+namespace gmsb {
+
+namespace {
+
+__global__ void k_init_degrees(const eid_t *__restrict__ off, int64_t n, int *__restrict__ deg) {
+    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x)
+        deg[v] = (int)(off[v + 1] - off[v]);
+}
+
+// frontier of level k: every live vertex with residual degree <= k
+__global__ void k_collect(int64_t n, int k, const int *__restrict__ deg, int *__restrict__ gone,
+                          vid_t *__restrict__ queue, int *__restrict__ qsize) {
+    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x)
+        if (!gone[v] && deg[v] <= k) {
+            gone[v] = 1;
+            queue[atomicAdd(qsize, 1)] = (vid_t)v;
+        }
+}
+
+__global__ void k_assign_rank(const vid_t *__restrict__ queue, int qs, int64_t n, int64_t done,
+                              vid_t *__restrict__ rank) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < qs; i += gridDim.x * blockDim.x)
+        rank[queue[i]] = (vid_t)(n - 1 - (done + i));
+}
+
+// one warp per frontier vertex: decrement live neighbours; those that reach <= k join the next frontier
+__global__ void k_relax(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, const vid_t *__restrict__ queue,
+                        int qs, int k, int *__restrict__ deg, int *__restrict__ gone, vid_t *__restrict__ next,
+                        int *__restrict__ nsize) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = warp; i < qs; i += nwarps) {
+        const vid_t v = queue[i];
+        for (eid_t e = off[v] + lane; e < off[v + 1]; e += 32) {
+            const vid_t w = nbr[e];
+            if (gone[w]) continue;
+            const int old = atomicSub(&deg[w], 1);
+            if (old - 1 <= k && atomicExch(&gone[w], 1) == 0) next[atomicAdd(nsize, 1)] = w;
+        }
+    }
+}
+
+}  // namespace
+
+void degeneracy_rank(Graph &g, vid_t *out_rank) {
+    GMSB_REQUIRE(!g.directed, "order_degeneracy: graph must be undirected");
+    Runtime &r = rt();
+    const int64_t n = g.n;
+    if (n == 0) return;
+    GMSB_REQUIRE(n < (int64_t(1) << 31), "order_degeneracy: too many vertices");
+    DevBuf<int> deg(n), gone(n), sizes(2);
+    DevBuf<vid_t> qa(n), qb(n), rank(n);
+    gone.zero();
+    k_init_degrees<<<grid_for(n, 256), 256, 0, r.stream>>>(g.off.p, n, deg.p); launched();
+    int64_t done = 0;
+    for (int k = 0; done < n; ++k) {
+        sizes.zero();
+        k_collect<<<grid_for(n, 256), 256, 0, r.stream>>>(n, k, deg.p, gone.p, qa.p, sizes.p); launched();
+        vid_t *cur = qa.p, *nxt = qb.p;
+        int *cs = sizes.p, *ns = sizes.p + 1;
+        for (;;) {
+            int qs = 0;
+            GMSB_CUDA(cudaMemcpyAsync(&qs, cs, sizeof(int), cudaMemcpyDeviceToHost, r.stream));
+            GMSB_CUDA(cudaStreamSynchronize(r.stream));
+            if (qs == 0) break;
+            k_assign_rank<<<grid_for(qs, 256), 256, 0, r.stream>>>(cur, qs, n, done, rank.p); launched();
+            done += qs;
+            GMSB_CUDA(cudaMemsetAsync(ns, 0, sizeof(int), r.stream));
+            k_relax<<<grid_for((int64_t)qs * 32, 256), 256, 0, r.stream>>>(g.off.p, g.nbr.p, cur, qs, k, deg.p, gone.p,
+                                                                           nxt, ns);
+            launched();
+            std::swap(cur, nxt);
+            std::swap(cs, ns);
+        }
+    }
+    rank.download(out_rank, n);
+}
+
+}  // namespace gmsb

@@ -15,8 +15,9 @@ void intersect_batch(Graph &g, int64_t np, const vid_t *a, const vid_t *b, int64
 void pair_similarity(Graph &g, int metric, int64_t np, const vid_t *a, const vid_t *b, double *out);
 void edge_similarity(Graph &g, int metric, double *out, int64_t *m_out);
 
-// tc_vertex.cu
+// tc_support.cu
 void tc_vertex2(Graph &g, int64_t *out_n);
+void edge_scores_from_support(Graph &g, int metric, const int64_t *base_dev, double *out_dev);
 
 // kcore.cu
 void degeneracy_rank(Graph &g, vid_t *out_rank);

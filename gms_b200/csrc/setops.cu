@@ -239,6 +239,14 @@ void edge_similarity(Graph &g, int metric, double *out, int64_t *m_out) {
     }
     if (m_out) *m_out = m;
     if (!out || m == 0) return;
+    if (metric != GMSB_SIM_ADAMIC_ADAR && metric != GMSB_SIM_RESOURCE) {
+        // these five depend on the graph only through |N(a) ∩ N(b)| = the edge's triangle support: one pass of the
+        // oriented triangle schedule instead of one symmetric intersection per edge (tc_support.cu)
+        DevBuf<double> dout(m);
+        edge_scores_from_support(g, metric, base.p, dout.p);
+        dout.download(out, m);
+        return;
+    }
     DevBuf<vid_t> pa(m), pb(m);
     k_emit_upper<<<grid_for(n * 32, 256), 256, 0, r.stream>>>(g.off.p, g.nbr.p, n, base.p, pa.p, pb.p); launched();
     pair_similarity_device(g, metric, m, pa.p, pb.p, out);

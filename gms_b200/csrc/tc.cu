@@ -20,38 +20,9 @@
 #include "sort.cuh"
 #include "orient.cuh"
 #include "isect.cuh"
+#include "tc_plan.cuh"
 
 namespace gmsb {
-
-constexpr int kLenBits = 24;                        // descriptor = (start << 24) | len
-constexpr uint64_t kLenMask = (1ull << kLenBits) - 1;
-
-struct Item {            // one CTA's share of a hub's incoming descriptors
-    int32_t v;
-    int32_t count;
-    int64_t begin;
-};
-
-struct TcPlan {
-    gmsb_tc_options opt{};
-    int64_t n_desc = 0;                 // descriptors that can close a triangle
-    DevBuf<uint64_t> desc;              // grouped by v (ascending), by u inside a group
-    DevBuf<uint32_t> desc_v;            // v of each descriptor
-    DevBuf<Item> items;                 // bitmap work items
-    int64_t n_items = 0;
-    int max_span_words = 0;
-    DevBuf<uint64_t> m_desc, g_desc;    // light edges for merge / gallop
-    DevBuf<vid_t> m_v, g_v;
-    int64_t n_merge = 0, n_gallop = 0, n_bitmap_edges = 0;
-    uint64_t algorithmic_bytes = 0;     // B_TC over ALL oriented edges
-    uint64_t wedges = 0;
-    uint64_t bytes_bitmap = 0, bytes_kept = 0, wedges_bitmap = 0;
-    // backing stores of the sorted arrays (double buffers keep the result in either half)
-    DevBuf<uint32_t> keys_a, keys_b;
-    DevBuf<uint64_t> vals_a, vals_b;
-    uint32_t *sorted_keys = nullptr;
-    uint64_t *sorted_vals = nullptr;
-};
 
 void delete_plan(TcPlan *p) { delete p; }
 
@@ -59,7 +30,7 @@ namespace {
 
 // ---- plan construction -----------------------------------------------------------------------------------------
 // One warp per vertex u: a descriptor for every out-edge; edges that cannot close a triangle (empty suffix or
-// sink v) get the sentinel key n and sort to the tail.
+// sink v) get the sentinel key n<<2 and sort to the tail.
 __global__ void k_emit_desc(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, int64_t n,
                             uint32_t *__restrict__ keys, uint64_t *__restrict__ vals,
                             unsigned long long *__restrict__ work /* n: wedges arriving at v */,
@@ -75,15 +46,16 @@ __global__ void k_emit_desc(const eid_t *__restrict__ off, const vid_t *__restri
             vid_t v = nbr[s];
             eid_t dv = off[v + 1] - off[v];
             eid_t len = e - s - 1;
-            bytes += 4ull * (unsigned long long)((e - b) + dv);
+            unsigned long long eb = 4ull * (unsigned long long)((e - b) + dv);
+            bytes += eb;
             bool kp = len > 0 && dv > 0;
-            keys[s] = kp ? (uint32_t)v : (uint32_t)n;
+            uint32_t cls = len <= kShortLen ? 0u : (len <= kMidLen ? 1u : 2u);
+            keys[s] = kp ? (((uint32_t)v << kClassBits) | cls) : ((uint32_t)n << kClassBits);
             vals[s] = ((uint64_t)(s + 1) << kLenBits) | (uint64_t)len;
             if (kp) {
                 atomicAdd(&work[v], (unsigned long long)len);
-                atomicAdd(&vbytes[v], 4ull * (unsigned long long)((e - b) + dv));
-                wedges += len; kept++;
-                kbytes += 4ull * (unsigned long long)((e - b) + dv);
+                atomicAdd(&vbytes[v], eb);
+                wedges += len; kept++; kbytes += eb;
             }
         }
     }
@@ -93,19 +65,23 @@ __global__ void k_emit_desc(const eid_t *__restrict__ off, const vid_t *__restri
         kept += __shfl_xor_sync(0xffffffffu, kept, o);
         kbytes += __shfl_xor_sync(0xffffffffu, kbytes, o);
     }
-    if (lane == 0 && (bytes | kept)) { atomicAdd(&acc[0], bytes); atomicAdd(&acc[1], wedges); atomicAdd(&acc[2], kept); atomicAdd(&acc[3], kbytes); }
+    if (lane == 0 && (bytes | kept)) {
+        atomicAdd(&acc[0], bytes); atomicAdd(&acc[1], wedges); atomicAdd(&acc[2], kept); atomicAdd(&acc[3], kbytes);
+    }
 }
 
-// inoff[x] = first descriptor whose key >= x  (keys sorted ascending, length cnt)
-__global__ void k_lower_bounds(const uint32_t *__restrict__ keys, int64_t cnt, int64_t n, int64_t *__restrict__ inoff) {
-    for (int64_t x = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; x <= n; x += (int64_t)gridDim.x * blockDim.x) {
-        int64_t lo = 0, hi = cnt;
-        while (lo < hi) {
-            int64_t mid = (lo + hi) >> 1;
-            if ((int64_t)keys[mid] < x) lo = mid + 1; else hi = mid;
-        }
-        inoff[x] = lo;
+__device__ __forceinline__ int64_t first_key_ge(const uint32_t *__restrict__ keys, int64_t lo, int64_t hi, uint32_t x) {
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (keys[mid] < x) lo = mid + 1; else hi = mid;
     }
+    return lo;
+}
+
+// inoff[v] = first descriptor of vertex v (keys sorted ascending, length cnt); inoff[n] = cnt
+__global__ void k_vertex_bounds(const uint32_t *__restrict__ keys, int64_t cnt, int64_t n, int64_t *__restrict__ inoff) {
+    for (int64_t x = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; x <= n; x += (int64_t)gridDim.x * blockDim.x)
+        inoff[x] = first_key_ge(keys, 0, cnt, (uint32_t)x << kClassBits);
 }
 
 struct PlanParams {
@@ -150,21 +126,41 @@ __global__ void k_classify(const eid_t *__restrict__ off, const vid_t *__restric
     if ((threadIdx.x & 31) == 0 && mx) atomicMax(max_span_words, mx);
 }
 
-__global__ void k_fill_items(int64_t n, const int64_t *__restrict__ inoff, const int64_t *__restrict__ nitems,
-                             const int64_t *__restrict__ item_base, Item *__restrict__ items) {
+__global__ void k_fill_items(int64_t n, const uint32_t *__restrict__ keys, const int64_t *__restrict__ inoff,
+                             const int64_t *__restrict__ nitems, const int64_t *__restrict__ item_base,
+                             Item *__restrict__ items) {
     for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x) {
         int64_t k = nitems[v];
         if (!k) continue;
-        int64_t b = inoff[v], cnt = inoff[v + 1] - b;
+        int64_t b = inoff[v], e = inoff[v + 1], cnt = e - b;
+        int64_t c0 = first_key_ge(keys, b, e, ((uint32_t)v << kClassBits) | 1u);     // end of class 0
+        int64_t c1 = first_key_ge(keys, c0, e, ((uint32_t)v << kClassBits) | 2u);    // end of class 1
         int64_t chunk = (cnt + k - 1) / k;
         int64_t w = item_base[v];
         for (int64_t j = 0; j < k; ++j) {
-            int64_t s = j * chunk;
-            int64_t c = cnt - s < chunk ? cnt - s : chunk;
+            int64_t s = b + j * chunk;
+            int64_t c = e - s < chunk ? e - s : chunk;
+            if (c < 0) c = 0;
             Item it;
-            it.v = (int32_t)v; it.begin = b + s; it.count = (int32_t)(c > 0 ? c : 0);
+            it.v = (int32_t)v; it.begin = s; it.count = (int32_t)c;
+            int64_t a0 = c0 - s, a1 = c1 - s;
+            it.n0 = (int32_t)(a0 < 0 ? 0 : (a0 > c ? c : a0));
+            it.n1 = (int32_t)(a1 < 0 ? 0 : (a1 > c ? c : a1));
             items[w + j] = it;
         }
+    }
+}
+
+// Order key of an item: L2 tile of its first suffix (tile-major order keeps the lists that concurrently running
+// CTAs stream inside the L2), then heaviest vertex first.
+__global__ void k_item_keys(const Item *__restrict__ items, int64_t cnt, const uint64_t *__restrict__ desc, int64_t n,
+                            int tile_shift, uint64_t *__restrict__ keys) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < cnt; i += (int64_t)gridDim.x * blockDim.x) {
+        const Item it = items[i];
+        // a slice that mixes classes has no single u-range: use its longest-suffix part (the bulk of its work)
+        const int64_t d = it.begin + (it.n1 < it.count ? it.n1 : (it.n0 < it.count ? it.n0 : 0));
+        const uint64_t tile = tile_shift > 0 ? (desc[d] >> kLenBits) >> tile_shift : 0;
+        keys[i] = (tile << 32) | (uint64_t)(uint32_t)(n - 1 - it.v);
     }
 }
 
@@ -173,7 +169,7 @@ __global__ void k_flag_light(const uint32_t *__restrict__ keys, const uint64_t *
                              const eid_t *__restrict__ off, const int64_t *__restrict__ nitems, int variant,
                              int ratio, uint8_t *__restrict__ fm, uint8_t *__restrict__ fg) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < cnt; i += (int64_t)gridDim.x * blockDim.x) {
-        uint32_t v = keys[i];
+        uint32_t v = keys[i] >> kClassBits;
         bool light = nitems[v] == 0;
         bool gallop = false;
         if (light) {
@@ -190,7 +186,7 @@ __global__ void k_compact_light(const uint32_t *__restrict__ keys, const uint64_
                                 const uint8_t *__restrict__ flag, const int64_t *__restrict__ pos,
                                 uint64_t *__restrict__ odesc, vid_t *__restrict__ ov) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < cnt; i += (int64_t)gridDim.x * blockDim.x)
-        if (flag[i]) { odesc[pos[i]] = vals[i]; ov[pos[i]] = (vid_t)keys[i]; }
+        if (flag[i]) { odesc[pos[i]] = vals[i]; ov[pos[i]] = (vid_t)(keys[i] >> kClassBits); }
 }
 
 // ---- counting kernels ----------------------------------------------------------------------------------------------
@@ -198,13 +194,63 @@ __global__ void k_compact_light(const uint32_t *__restrict__ keys, const uint64_
 // suffix descriptors) from a global ticket, heaviest first.  The shared-memory bitmap is zeroed ONCE per CTA; each
 // item sets the bits of N+(v), streams its suffixes, then clears exactly the words it set — so the per-item cost
 // is O(d+(v)) and independent of how wide the window (v, last(N+(v))] is.  Inside an item the warps pull
-// descriptors from a shared-memory ticket (suffix lengths vary by 1000x), load list elements with coalesced
-// 4-deep unrolled loads and do ONE branch-free probe per element: out-of-window elements are clamped onto the
-// always-zero guard word bm[cap_words].
+// descriptors from shared-memory tickets, one per length class (suffix lengths vary by 1000x): a lane, an 8-lane
+// group or the whole warp takes one descriptor, so short suffixes do not pay a warp's worth of control overhead.
+// List elements are read with coalesced, 4-deep predicated loads and cost ONE branch-free probe each:
+// out-of-window elements (and predicated-off slots, x = ~0) are clamped onto the always-zero guard word.
 constexpr int kDescChunk = 4;
 
-__device__ __forceinline__ uint32_t probe(const uint32_t *bm, uint32_t x, uint32_t cap_words) {
-    return (bm[min(x >> 5, cap_words)] >> (x & 31)) & 1u;
+// G lanes cooperate on one descriptor; the warp takes 32/G descriptors per ticket (4 when G == 32).
+template <int G>
+__device__ __forceinline__ uint32_t stream_class(const uint64_t *__restrict__ dptr, int lo, int hi, int *ticket,
+                                                 const vid_t *__restrict__ nbr, const uint32_t *bm, uint32_t base,
+                                                 uint32_t cap_words, int lane) {
+    uint32_t hits = 0;
+    if (lo >= hi) return 0;
+    constexpr int BATCH = G == 32 ? kDescChunk : 32 / G;
+    for (;;) {
+        int d0 = 0;
+        if (lane == 0) d0 = atomicAdd(ticket, BATCH);
+        d0 = __shfl_sync(0xffffffffu, d0, 0) + lo;
+        if (d0 >= hi) break;
+        if constexpr (G == 32) {
+            const int nd = min(BATCH, hi - d0);
+            const uint64_t mine = lane < nd ? dptr[d0 + lane] : 0ull;
+            for (int k = 0; k < nd; ++k) {
+                const uint64_t ds = __shfl_sync(0xffffffffu, mine, k);
+                const vid_t *__restrict__ p = nbr + (ds >> kLenBits);
+                const int len = (int)(ds & kLenMask);
+                for (int j = lane; j < len; j += 128) {
+                    const uint32_t x0 = (uint32_t)p[j] - base;
+                    const uint32_t x1 = j + 32 < len ? (uint32_t)p[j + 32] - base : ~0u;
+                    const uint32_t x2 = j + 64 < len ? (uint32_t)p[j + 64] - base : ~0u;
+                    const uint32_t x3 = j + 96 < len ? (uint32_t)p[j + 96] - base : ~0u;
+                    hits += probe(bm, x0, cap_words) + probe(bm, x1, cap_words) + probe(bm, x2, cap_words) +
+                            probe(bm, x3, cap_words);
+                }
+            }
+        } else {
+            const int idx = d0 + lane / G, sub = lane % G;
+            const uint64_t ds = idx < hi ? dptr[idx] : 0ull;
+            const vid_t *__restrict__ p = nbr + (ds >> kLenBits);
+            const int len = (int)(ds & kLenMask);
+            if constexpr (G == 1) {
+#pragma unroll
+                for (int j = 0; j < kShortLen; ++j)
+                    hits += probe(bm, j < len ? (uint32_t)p[j] - base : ~0u, cap_words);
+            } else {
+                for (int j = sub; j < len; j += 4 * G) {
+                    const uint32_t x0 = (uint32_t)p[j] - base;
+                    const uint32_t x1 = j + G < len ? (uint32_t)p[j + G] - base : ~0u;
+                    const uint32_t x2 = j + 2 * G < len ? (uint32_t)p[j + 2 * G] - base : ~0u;
+                    const uint32_t x3 = j + 3 * G < len ? (uint32_t)p[j + 3 * G] - base : ~0u;
+                    hits += probe(bm, x0, cap_words) + probe(bm, x1, cap_words) + probe(bm, x2, cap_words) +
+                            probe(bm, x3, cap_words);
+                }
+            }
+        }
+    }
+    return hits;
 }
 
 template <int BLOCK, int MINB>
@@ -215,16 +261,16 @@ k_tc_bitmap(const Item *__restrict__ items, int64_t first, int64_t stride, int64
     extern __shared__ uint32_t bm[];                  // cap_words + 1 words
     __shared__ unsigned long long red[BLOCK / 32];
     __shared__ unsigned int s_item;
-    __shared__ int s_next;
+    __shared__ int s_next[3];
     const int tid = threadIdx.x, lane = tid & 31;
     for (uint32_t i = tid; i <= cap_words; i += BLOCK) bm[i] = 0u;
     unsigned long long hits64 = 0;
     for (;;) {
-        if (tid == 0) { s_item = atomicAdd(ticket, 1u); s_next = 0; }
+        if (tid == 0) { s_item = atomicAdd(ticket, 1u); s_next[0] = 0; s_next[1] = 0; s_next[2] = 0; }
         __syncthreads();                              // ticket visible; previous item's clears done
         const int64_t it = (int64_t)s_item;
         if (it >= count) break;
-        const Item item = items[first + (count - 1 - it) * stride];        // heaviest (highest v) first
+        const Item item = items[first + it * stride];                     // plan order: L2 tile, then heaviest
         const vid_t v = item.v;
         const eid_t ob = off[v], oe = off[v + 1];
         const uint32_t base = (uint32_t)v + 1u;
@@ -233,31 +279,10 @@ k_tc_bitmap(const Item *__restrict__ items, int64_t first, int64_t stride, int64
             atomicOr(&bm[x >> 5], 1u << (x & 31));
         }
         __syncthreads();                              // bitmap of N+(v) complete
-
-        uint32_t hits = 0;
         const uint64_t *__restrict__ dptr = desc + item.begin;
-        const int cnt = item.count;
-        for (;;) {
-            int d0 = 0;
-            if (lane == 0) d0 = atomicAdd(&s_next, kDescChunk);
-            d0 = __shfl_sync(0xffffffffu, d0, 0);
-            if (d0 >= cnt) break;
-            const int nd = min(kDescChunk, cnt - d0);
-            const uint64_t mine = lane < nd ? dptr[d0 + lane] : 0ull;
-            for (int k = 0; k < nd; ++k) {
-                const uint64_t ds = __shfl_sync(0xffffffffu, mine, k);
-                const vid_t *__restrict__ p = nbr + (ds >> kLenBits);
-                const int len = (int)(ds & kLenMask);
-                int j = lane;
-                for (; j + 96 < len; j += 128) {      // 4 independent loads in flight per lane
-                    const uint32_t x0 = (uint32_t)p[j] - base, x1 = (uint32_t)p[j + 32] - base;
-                    const uint32_t x2 = (uint32_t)p[j + 64] - base, x3 = (uint32_t)p[j + 96] - base;
-                    hits += probe(bm, x0, cap_words) + probe(bm, x1, cap_words) + probe(bm, x2, cap_words) +
-                            probe(bm, x3, cap_words);
-                }
-                for (; j < len; j += 32) hits += probe(bm, (uint32_t)p[j] - base, cap_words);
-            }
-        }
+        uint32_t hits = stream_class<32>(dptr, item.n1, item.count, &s_next[2], nbr, bm, base, cap_words, lane);
+        hits += stream_class<8>(dptr, item.n0, item.n1, &s_next[1], nbr, bm, base, cap_words, lane);
+        hits += stream_class<1>(dptr, 0, item.n0, &s_next[0], nbr, bm, base, cap_words, lane);
         hits64 += hits;
         __syncthreads();                              // every probe of this item done
         for (eid_t j = ob + tid; j < oe; j += BLOCK) bm[((uint32_t)nbr[j] - base) >> 5] = 0u;
@@ -319,13 +344,13 @@ gmsb_tc_options normalise(const gmsb_tc_options *in) {
     if (o.part_count <= 0) { o.part_count = 1; o.part_index = 0; }
     if (o.hub_bitmap_bits <= 0) o.hub_bitmap_bits = 512 * 1024;      // 64 KB of shared memory
     if (o.gallop_ratio <= 0) o.gallop_ratio = 8;
-    if (o.hub_min_work <= 0) o.hub_min_work = 4096;
+    if (o.hub_min_work <= 0) o.hub_min_work = 1024;
     return o;
 }
 
 bool same_plan(const gmsb_tc_options &a, const gmsb_tc_options &b) {
     return a.variant == b.variant && a.hub_bitmap_bits == b.hub_bitmap_bits && a.gallop_ratio == b.gallop_ratio &&
-           a.hub_min_work == b.hub_min_work && a.reserved[0] == b.reserved[0];
+           a.hub_min_work == b.hub_min_work && a.reserved[0] == b.reserved[0] && a.reserved[1] == b.reserved[1];
 }
 
 TcPlan *build_plan(const Dag &d, const gmsb_tc_options &opt) {
@@ -336,6 +361,7 @@ TcPlan *build_plan(const Dag &d, const gmsb_tc_options &opt) {
         const int64_t n = d.n, m = d.m;
         GMSB_REQUIRE(d.max_dplus < (1 << kLenBits), "tc: out-degree too large for the descriptor format");
         GMSB_REQUIRE(m < (int64_t(1) << (64 - kLenBits)), "tc: too many edges for the descriptor format");
+        GMSB_REQUIRE(n < (int64_t(1) << (32 - kClassBits)), "tc: too many vertices for the 32-bit schedule key");
         size_t smem_cap = r.smem_optin ? r.smem_optin : 48 * 1024;
         int hub_bits = opt.hub_bitmap_bits;
         if ((size_t)hub_bits / 8 > smem_cap - 1024) hub_bits = (int)((smem_cap - 1024) * 8);
@@ -347,25 +373,25 @@ TcPlan *build_plan(const Dag &d, const gmsb_tc_options &opt) {
         k_emit_desc<<<grid_for(n * 32, 256), 256, 0, r.stream>>>(d.off.p, d.nbr.p, n, p->keys_a.p, p->vals_a.p,
                                                                  work.p, vbytes.p, acc.p);
         launched();
-        radix_sort_pairs(p->keys_a.p, p->keys_b.p, p->vals_a.p, p->vals_b.p, m, bits_for((uint64_t)n),
+        radix_sort_pairs(p->keys_a.p, p->keys_b.p, p->vals_a.p, p->vals_b.p, m, bits_for((uint64_t)n) + kClassBits,
                          &p->sorted_keys, &p->sorted_vals);
         unsigned long long h_acc[4];
         acc.download(h_acc, 4);
-        p->bytes_kept = h_acc[3];
         p->algorithmic_bytes = h_acc[0];
         p->wedges = h_acc[1];
         p->n_desc = (int64_t)h_acc[2];
+        p->bytes_kept = h_acc[3];
         const int64_t cnt = p->n_desc;
         if (cnt == 0) return p;
 
         DevBuf<int64_t> inoff(n + 1), nitems(n + 1), item_base(n + 1);
-        k_lower_bounds<<<grid_for(n + 1, 256), 256, 0, r.stream>>>(p->sorted_keys, cnt, n, inoff.p); launched();
+        k_vertex_bounds<<<grid_for(n + 1, 256), 256, 0, r.stream>>>(p->sorted_keys, cnt, n, inoff.p); launched();
         DevBuf<int> mxw(1);
         mxw.zero(); nitems.zero();
         PlanParams pp{opt.variant, hub_bits, (long long)opt.hub_min_work,
                       opt.reserved[0] > 0 ? (long long)opt.reserved[0] : 262144ll};
-        k_classify<<<grid_for(n, 256), 256, 0, r.stream>>>(d.off.p, d.nbr.p, n, inoff.p, work.p, vbytes.p, cls.p, pp, nitems.p,
-                                                          mxw.p);
+        k_classify<<<grid_for(n, 256), 256, 0, r.stream>>>(d.off.p, d.nbr.p, n, inoff.p, work.p, vbytes.p, cls.p, pp,
+                                                          nitems.p, mxw.p);
         launched();
         exclusive_sum(nitems.p, item_base.p, n + 1);
         p->n_items = item_base.get(n);
@@ -376,8 +402,25 @@ TcPlan *build_plan(const Dag &d, const gmsb_tc_options &opt) {
         p->wedges_bitmap = h_cls[1];
         if (p->n_items) {
             p->items.alloc(p->n_items);
-            k_fill_items<<<grid_for(n, 256), 256, 0, r.stream>>>(n, inoff.p, nitems.p, item_base.p, p->items.p);
+            k_fill_items<<<grid_for(n, 256), 256, 0, r.stream>>>(n, p->sorted_keys, inoff.p, nitems.p, item_base.p,
+                                                                p->items.p);
             launched();
+            // order: tile-major, heaviest first inside a tile
+            DevBuf<uint64_t> ik(p->n_items), ik2(p->n_items);
+            DevBuf<Item> items2(p->n_items);
+            const int tile_shift = opt.reserved[1] > 0 ? opt.reserved[1] : (opt.reserved[1] < 0 ? 0 : 24);
+            k_item_keys<<<grid_for(p->n_items, 256), 256, 0, r.stream>>>(p->items.p, p->n_items, p->sorted_vals, n,
+                                                                        tile_shift, ik.p);
+            launched();
+            size_t bytes = 0;
+            GMSB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, ik.p, ik2.p, p->items.p, items2.p, p->n_items, 0,
+                                                      64, r.stream));
+            DevBuf<uint8_t> tmp(bytes);
+            GMSB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, ik.p, ik2.p, p->items.p, items2.p, p->n_items, 0,
+                                                      64, r.stream));
+            r.launches += 9;
+            GMSB_CUDA(cudaStreamSynchronize(r.stream));
+            p->items = std::move(items2);
         }
         // light edges -> two compacted lists
         DevBuf<uint8_t> fm(cnt), fg(cnt);
@@ -414,23 +457,31 @@ int64_t part_size(int64_t total, int idx, int parts) { return total > idx ? (tot
 
 }  // namespace
 
+gmsb_tc_options normalise_tc_options(const gmsb_tc_options *in) { return normalise(in); }
+
+TcPlan &ensure_plan(Graph &g, const gmsb_tc_options &opt) {
+    GMSB_REQUIRE(!g.directed, "triangle kernels need an undirected graph");
+    GMSB_REQUIRE(opt.variant >= GMSB_TC_AUTO && opt.variant <= GMSB_TC_BITMAP, "tc: bad variant");
+    if (!opt.reuse_plan) { delete g.dag; g.dag = nullptr; }
+    if (!g.dag) g.dag = build_degree_dag(g);
+    Dag &d = *g.dag;
+    if (d.plan && !same_plan(d.plan->opt, opt)) { delete_plan(d.plan); d.plan = nullptr; }
+    if (!d.plan) d.plan = build_plan(d, opt);
+    return *d.plan;
+}
+
 void tc_total(Graph &g, const gmsb_tc_options &opt_in, uint64_t *out, gmsb_tc_stats *stats) {
     GMSB_REQUIRE(!g.directed, "tc_total: graph must be undirected");
     GMSB_REQUIRE(out != nullptr, "tc_total: null output");
     Runtime &r = rt();
     gmsb_tc_options opt = normalise(&opt_in);
     GMSB_REQUIRE(opt.part_index >= 0 && opt.part_index < opt.part_count, "tc_total: bad partition");
-    GMSB_REQUIRE(opt.variant >= GMSB_TC_AUTO && opt.variant <= GMSB_TC_BITMAP, "tc_total: bad variant");
     const uint64_t launches0 = r.launches;
     DevTimer t_orient, t_bm, t_mg, t_gl;
 
     t_orient.start();
-    if (!opt.reuse_plan) { delete g.dag; g.dag = nullptr; }
-    if (!g.dag) g.dag = build_degree_dag(g);
+    TcPlan &p = ensure_plan(g, opt);
     Dag &d = *g.dag;
-    if (d.plan && !same_plan(d.plan->opt, opt)) { delete_plan(d.plan); d.plan = nullptr; }
-    if (!d.plan) d.plan = build_plan(d, opt);
-    TcPlan &p = *d.plan;
     t_orient.stop();
 
     DevBuf<unsigned long long> total(1);
@@ -442,8 +493,13 @@ void tc_total(Graph &g, const gmsb_tc_options &opt_in, uint64_t *out, gmsb_tc_st
 
     t_bm.start();
     if (my_items) {
-        constexpr int BLOCK = 512, MINB = 3;
-        auto kern = k_tc_bitmap<BLOCK, MINB>;
+        // CTA shape: 512 threads x 3 resident CTAs by default; reserved[2] picks another shape for experiments
+        int BLOCK = 512;
+        auto kern = k_tc_bitmap<512, 3>;
+        if (opt.reserved[2] == 1) { BLOCK = 256; kern = k_tc_bitmap<256, 6>; }
+        else if (opt.reserved[2] == 2) { BLOCK = 1024; kern = k_tc_bitmap<1024, 1>; }
+        else if (opt.reserved[2] == 3) { BLOCK = 512; kern = k_tc_bitmap<512, 4>; }
+        else if (opt.reserved[2] == 4) { BLOCK = 256; kern = k_tc_bitmap<256, 8>; }
         const size_t smem = ((size_t)p.max_span_words + 1) * 4;
         if (smem > 48 * 1024)
             GMSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -493,10 +549,10 @@ void tc_total(Graph &g, const gmsb_tc_options &opt_in, uint64_t *out, gmsb_tc_st
         s.launches = (int32_t)(r.launches - launches0);
         s.max_dplus = d.max_dplus;
         s.bytes_bitmap = p.bytes_bitmap;
-        s.wedges_bitmap = p.wedges_bitmap;
         s.bytes_light = p.bytes_kept - p.bytes_bitmap;
+        s.wedges_bitmap = p.wedges_bitmap;
         s.bitmap_items = p.n_items;
-        s.bitmap_smem_bytes = p.max_span_words * 4;
+        s.bitmap_smem_bytes = (p.max_span_words + 1) * 4;
         *stats = s;
     }
     if (!opt.reuse_plan) { delete g.dag; g.dag = nullptr; }

@@ -174,6 +174,7 @@ class CpuLib:
                 "rmat_el": (None, [C.c_int, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_int, _i32p, _i32p]),
                 "degeneracy_rank": (None, [C.c_void_p, _i32p]),
                 "check_degeneracy_rank": (C.c_int64, [C.c_void_p, _i32p]),
+                "core_number_of_rank": (C.c_int64, [C.c_void_p, _i32p]),
                 "tc_bytes": (None, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                     C.POINTER(C.c_int64)]),
             })
@@ -264,6 +265,9 @@ class CpuLib:
 
     def check_degeneracy_rank(self, g, rank):
         return int(self._f("check_degeneracy_rank")(g.h, np.ascontiguousarray(rank, np.int32)))
+
+    def core_number_of_rank(self, g, rank):
+        return int(self._f("core_number_of_rank")(g.h, np.ascontiguousarray(rank, np.int32)))
 
     def tc_bytes(self, g):
         bt, br, mx = C.c_uint64(0), C.c_uint64(0), C.c_int64(0)

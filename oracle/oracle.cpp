@@ -485,6 +485,25 @@ double orc_tc_total_sample(void *h, int64_t stride, int64_t phase, int64_t *edge
 void orc_degree_order(void *h, int rank_format, int32_t *out) { degree_order(*G(h), rank_format != 0, out); }
 void orc_degeneracy_rank(void *h, int32_t *rank_out) { degeneracy_rank(*G(h), rank_out); }
 int64_t orc_check_degeneracy_rank(void *h, const int32_t *rank) { return check_degeneracy_rank(*G(h), rank); }
+// The reference's own acceptance test for a degeneracy order (verifiers/degeneracy_verifier.h:69-85), in rank
+// format: with removal order = descending rank, every vertex may have at most `degeneracy` neighbours removed
+// after it.  Returns max_v |{w in N(v): rank[w] < rank[v]}| (the "core number of the order"), or -1 if rank is
+// not a permutation.  A valid order returns exactly the degeneracy.
+int64_t orc_core_number_of_rank(void *h, const int32_t *rank) {
+    const Graph &g = *G(h);
+    std::vector<char> seen(g.n, 0);
+    for (int64_t v = 0; v < g.n; ++v) {
+        if (rank[v] < 0 || rank[v] >= g.n || seen[rank[v]]) return -1;
+        seen[rank[v]] = 1;
+    }
+    int64_t worst = 0;
+    for (int64_t v = 0; v < g.n; ++v) {
+        int64_t later = 0;
+        for (const vid *p = g.begin((vid)v); p != g.end((vid)v); ++p) later += rank[*p] < rank[v];
+        worst = std::max(worst, later);
+    }
+    return worst;
+}
 void *orc_induce_directed(void *h, const int32_t *ranking) { return new Graph(induce_directed(*G(h), ranking)); }
 
 uint64_t orc_kclique(void *h, int k, int /*mode*/) { return dag_cliques(*G(h), k); }
