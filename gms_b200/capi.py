@@ -54,6 +54,7 @@ SIGNATURES = {
     "gmsb_set_device": (C.c_int, [C.c_int]),
     "gmsb_set_stream": (C.c_int, [C.c_void_p]),
     "gmsb_synchronize": (C.c_int, []),
+    "gmsb_trim_memory": (C.c_int, []),
     "gmsb_launch_count": (C.c_int, [C.POINTER(C.c_uint64)]),
     "gmsb_generate_rmat": (C.c_int, [C.c_int, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_int, _i32p, _i32p]),
     "gmsb_generate_uniform": (C.c_int, [C.c_int, C.c_int64, _i32p, _i32p]),

@@ -6,6 +6,8 @@
 
 #include <cstring>
 #include <mutex>
+#include <unordered_map>
+#include <vector>
 
 namespace gmsb {
 
@@ -35,14 +37,64 @@ Runtime &rt() {
             g_rt.device = g_device;
             g_rt.sm_count = prop.multiProcessorCount;
             g_rt.smem_optin = prop.sharedMemPerBlockOptin;
-            cudaMemPool_t pool;
-            GMSB_CUDA(cudaDeviceGetDefaultMemPool(&pool, g_device));
-            uint64_t keep = UINT64_MAX;
-            GMSB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
             g_rt_ready = true;
         }
     }
     return g_rt;
+}
+
+// ---- caching device arena ------------------------------------------------------------------------------------------
+namespace {
+std::mutex g_arena_mutex;
+std::unordered_map<size_t, std::vector<void *>> g_arena_free;     // size class -> cached blocks
+std::unordered_map<void *, size_t> g_arena_live;                  // block -> size class
+
+// classes are spaced 12.5 % apart (and at least 512 B), so a block is at most 1/8 larger than requested
+size_t arena_class(size_t bytes) {
+    if (bytes <= 512) return 512;
+    int top = 63 - __builtin_clzll((unsigned long long)bytes);
+    size_t step = size_t(1) << (top > 3 ? top - 3 : 0);
+    if (step < 512) step = 512;
+    return (bytes + step - 1) / step * step;
+}
+}  // namespace
+
+void *arena_alloc(size_t bytes) {
+    rt();
+    const size_t cls = arena_class(bytes);
+    std::lock_guard<std::mutex> lock(g_arena_mutex);
+    auto &bin = g_arena_free[cls];
+    void *p = nullptr;
+    if (!bin.empty()) {
+        p = bin.back();
+        bin.pop_back();
+    } else {
+        cudaError_t e = cudaMalloc(&p, cls);
+        if (e == cudaErrorMemoryAllocation) {           // give the cache back and retry once
+            cudaGetLastError();
+            for (auto &kv : g_arena_free) { for (void *q : kv.second) cudaFree(q); kv.second.clear(); }
+            e = cudaMalloc(&p, cls);
+        }
+        if (e != cudaSuccess)
+            throw Error(e == cudaErrorMemoryAllocation ? GMSB_ERR_OOM : GMSB_ERR_CUDA,
+                        std::string("cudaMalloc(") + std::to_string(cls) + " bytes): " + cudaGetErrorString(e));
+    }
+    g_arena_live[p] = cls;
+    return p;
+}
+
+void arena_free(void *p) {
+    std::lock_guard<std::mutex> lock(g_arena_mutex);
+    auto it = g_arena_live.find(p);
+    if (it == g_arena_live.end()) return;
+    g_arena_free[it->second].push_back(p);
+    g_arena_live.erase(it);
+}
+
+void arena_trim() {
+    std::lock_guard<std::mutex> lock(g_arena_mutex);
+    cudaDeviceSynchronize();
+    for (auto &kv : g_arena_free) { for (void *q : kv.second) cudaFree(q); kv.second.clear(); }
 }
 
 template <typename F>
@@ -107,6 +159,7 @@ GMSB_API int gmsb_set_stream(void *s) {
         rt().stream = reinterpret_cast<cudaStream_t>(s);
     });
 }
+GMSB_API int gmsb_trim_memory(void) { return guarded([&] { arena_trim(); }); }
 GMSB_API int gmsb_synchronize(void) { return guarded([&] { GMSB_CUDA(cudaStreamSynchronize(rt().stream)); }); }
 GMSB_API int gmsb_launch_count(uint64_t *count) {
     return guarded([&] { GMSB_REQUIRE(count, "null argument"); *count = g_rt_ready ? g_rt.launches : 0; });

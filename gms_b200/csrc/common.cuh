@@ -44,6 +44,9 @@ struct Runtime {
 };
 Runtime &rt();             // lazily initialised; throws GMSB_ERR_CUDA when no device is usable
 void set_last_error(const std::string &msg);
+void *arena_alloc(size_t bytes);   // caching device allocator (size-class free lists over cudaMalloc)
+void arena_free(void *p);
+void arena_trim();                 // give every cached block back to the driver
 
 // Count a kernel launch (bench.py reports the total as gpu_launches) and surface launch errors early.
 inline void launched() {
@@ -65,16 +68,18 @@ struct DevBuf {
         return *this;
     }
     ~DevBuf() { release(); }
-    // Stream-ordered allocation from the device's default memory pool, whose release threshold rt() raises to
-    // "never": the multi-GB scratch of a graph build is recycled by the next build instead of being unmapped and
-    // re-mapped by the driver (cudaMalloc/cudaFree of GBs costs more than the kernels they feed).
+    // Allocation goes through the library's caching arena (capi.cu: arena_alloc / arena_free): freed blocks are
+    // kept in size-class free lists and handed out again, so the multi-GB scratch of a graph build is recycled by
+    // the next build instead of being unmapped and re-mapped by the driver — cudaMalloc/cudaFree (and the
+    // re-mapping a cudaMallocAsync pool does when sizes change) cost more than the kernels they feed.  All work is
+    // on one stream, so reuse of a freed block is ordered after its last use.
     void alloc(size_t count) {
         release();
         n = count;
-        if (count) GMSB_CUDA(cudaMallocAsync(&p, count * sizeof(T), rt().stream));
+        if (count) p = static_cast<T *>(arena_alloc(count * sizeof(T)));
     }
     void release() {
-        if (p) cudaFreeAsync(p, rt().stream);
+        if (p) arena_free(p);
         p = nullptr; n = 0;
     }
     void zero() { if (n) GMSB_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), rt().stream)); }

@@ -13,6 +13,8 @@
 #include "isect.cuh"
 #include "orient.cuh"
 
+#include <cstdlib>
+
 namespace gmsb {
 
 namespace {
@@ -103,6 +105,112 @@ __global__ void k_check_perm(const vid_t *__restrict__ rank, int64_t n, int *__r
     }
 }
 
+// ---- fast path: per-list sort on chip instead of a global 64-bit radix sort -----------------------------------
+// (1) relabel + count: rnbr[s] = rank[nbr[s]] is stored so that the emit pass streams instead of gathering again.
+__global__ void k_relabel_count(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, int64_t n,
+                                const vid_t *__restrict__ rank, vid_t *__restrict__ rnbr, eid_t *__restrict__ cnt) {
+    int lane = threadIdx.x & 31;
+    int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t u = warp; u < n; u += nwarps) {
+        eid_t b = off[u], e = off[u + 1];
+        vid_t ru = rank[u];
+        int c = 0;
+        for (eid_t s = b + lane; s < e; s += 32) {
+            vid_t rv = rank[nbr[s]];
+            rnbr[s] = rv;
+            c += rv > ru;
+        }
+        for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (lane == 0) cnt[ru + 1] = c;
+    }
+}
+
+__device__ __forceinline__ vid_t warp_bitonic_sort(vid_t v, int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const vid_t other = __shfl_xor_sync(0xffffffffu, v, j);
+            const bool up = (lane & k) == 0, lower = (lane & j) == 0;
+            v = (lower == up) ? min(v, other) : max(v, other);
+        }
+    }
+    return v;
+}
+
+// (2) emit: one warp per vertex compacts the higher-ranked neighbours with ballots.  Lists of <= 32 survivors are
+// sorted in registers (shuffle bitonic network) and written in final order; longer ones are written unsorted and
+// queued for the CTA sorter.
+__global__ void __launch_bounds__(256)
+k_emit_sorted(const eid_t *__restrict__ off, const vid_t *__restrict__ rnbr, int64_t n, const vid_t *__restrict__ rank,
+              const eid_t *__restrict__ doff, vid_t *__restrict__ dnbr, vid_t *__restrict__ big, int *__restrict__ nbig) {
+    __shared__ vid_t stage[8][32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t u = warp; u < n; u += nwarps) {
+        const vid_t ru = rank[u];
+        const eid_t ob = doff[ru];
+        const int c = (int)(doff[ru + 1] - ob);
+        if (c == 0) continue;
+        const eid_t b = off[u], e = off[u + 1];
+        const bool small = c <= 32;
+        int w = 0;
+        __syncwarp();
+        for (eid_t s0 = b; s0 < e; s0 += 32) {
+            const eid_t s = s0 + lane;
+            const vid_t rv = s < e ? rnbr[s] : -1;
+            const bool kp = rv > ru;
+            const unsigned mask = __ballot_sync(0xffffffffu, kp);
+            if (kp) {
+                const int p = w + __popc(mask & ((1u << lane) - 1));
+                if (small) stage[wib][p] = rv; else dnbr[ob + p] = rv;
+            }
+            w += __popc(mask);
+        }
+        if (small) {
+            __syncwarp();
+            vid_t v = lane < c ? stage[wib][lane] : 0x7fffffff;
+            v = warp_bitonic_sort(v, lane);
+            if (lane < c) dnbr[ob + lane] = v;
+        } else if (lane == 0) {
+            big[atomicAdd(nbig, 1)] = ru;
+        }
+    }
+}
+
+// (3) CTA sorter for the queued lists: bitonic network in shared memory, sized per list.
+constexpr int kSortCap = 8192;
+__global__ void __launch_bounds__(256)
+k_sort_big(const vid_t *__restrict__ big, int nbig, const eid_t *__restrict__ doff, vid_t *__restrict__ dnbr) {
+    extern __shared__ vid_t buf[];
+    for (int t = blockIdx.x; t < nbig; t += gridDim.x) {
+        const vid_t ru = big[t];
+        const eid_t ob = doff[ru];
+        const int c = (int)(doff[ru + 1] - ob);
+        int P = 64;
+        while (P < c) P <<= 1;
+        __syncthreads();
+        for (int i = threadIdx.x; i < P; i += blockDim.x) buf[i] = i < c ? dnbr[ob + i] : 0x7fffffff;
+        __syncthreads();
+        for (int k = 2; k <= P; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = threadIdx.x; i < P; i += blockDim.x) {
+                    const int x = i ^ j;
+                    if (x > i) {
+                        const vid_t a = buf[i], bq = buf[x];
+                        const bool up = (i & k) == 0;
+                        if ((a > bq) == up) { buf[i] = bq; buf[x] = a; }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        for (int i = threadIdx.x; i < c; i += blockDim.x) dnbr[ob + i] = buf[i];
+    }
+}
+
 }  // namespace
 
 void degree_order(const Graph &g, DevBuf<vid_t> &order, DevBuf<vid_t> &rank) {
@@ -123,25 +231,48 @@ void orient_by_rank(const Graph &g, const vid_t *rank_dev, DevBuf<eid_t> &doff, 
     int64_t n = g.n;
     doff.alloc(n + 1);
     doff.zero();
+    DevBuf<vid_t> rnbr(g.slots);
     if (n) {
-        k_count_out<<<grid_for(n * 32, 256), 256, 0, r.stream>>>(g.off.p, g.nbr.p, n, rank_dev, doff.p); launched();
+        k_relabel_count<<<grid_for(n * 32, 256), 256, 0, r.stream>>>(g.off.p, g.nbr.p, n, rank_dev, rnbr.p, doff.p);
+        launched();
         inclusive_sum_inplace(doff.p, n + 1);
     }
     int64_t m = n ? doff.get(n) : 0;
     *m_out = m;
     dnbr.alloc(m);
-    if (m) {
+    int maxd = 0;
+    if (n) {
+        DevBuf<int> mx(1);
+        mx.zero();
+        k_max_deg<<<grid_for(n, 256), 256, 0, r.stream>>>(doff.p, n, mx.p); launched();
+        maxd = mx.get(0);
+    }
+    if (max_dplus) *max_dplus = maxd;
+    if (m == 0) return;
+    int cap = kSortCap;
+    if (const char *env = getenv("GMSB_ORIENT_SORT_CAP")) cap = std::min(kSortCap, std::max(0, atoi(env)));   // tests
+    if (maxd <= cap) {
+        // lists sorted on chip: registers (<= 32) or shared memory; one streaming pass in, one out
+        DevBuf<vid_t> big(n);
+        DevBuf<int> nbig(1);
+        nbig.zero();
+        k_emit_sorted<<<grid_for(n * 32, 256), 256, 0, r.stream>>>(g.off.p, rnbr.p, n, rank_dev, doff.p, dnbr.p, big.p,
+                                                                  nbig.p);
+        launched();
+        const int nb = nbig.get(0);
+        if (nb) {
+            int P = 64;
+            while (P < maxd) P <<= 1;
+            const int grid = (int)std::min<int64_t>(nb, (int64_t)r.sm_count * 16);
+            k_sort_big<<<grid, 256, (size_t)P * sizeof(vid_t), r.stream>>>(big.p, nb, doff.p, dnbr.p); launched();
+        }
+    } else {
+        // general fallback for lists longer than the on-chip sorter: one global radix sort of (rank[u], rank[v]) keys
         DevBuf<uint64_t> keys(m), alt(m);
         k_emit_out<<<grid_for(n * 32, 256), 256, 0, r.stream>>>(g.off.p, g.nbr.p, n, rank_dev, doff.p, keys.p);
         launched();
         uint64_t *sorted = radix_sort_keys(keys.p, alt.p, m, 0, 32 + bits_for((uint64_t)(n - 1)));
         k_low32<<<grid_for(m, 256), 256, 0, r.stream>>>(sorted, m, dnbr.p); launched();
-    }
-    if (max_dplus) {
-        DevBuf<int> mx(1);
-        mx.zero();
-        if (n) { k_max_deg<<<grid_for(n, 256), 256, 0, r.stream>>>(doff.p, n, mx.p); launched(); }
-        *max_dplus = mx.get(0);
     }
 }
 

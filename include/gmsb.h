@@ -49,6 +49,9 @@ GMSB_API int gmsb_device_count(int *count);
 GMSB_API int gmsb_set_device(int device);
 GMSB_API int gmsb_set_stream(void *cuda_stream);            /* cudaStream_t; NULL = legacy default stream */
 GMSB_API int gmsb_synchronize(void);
+/* Device memory is cached in size-class free lists between calls (driver allocation of GBs costs more than the
+ * kernels); this returns every cached block to the driver. */
+GMSB_API int gmsb_trim_memory(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 GMSB_API int gmsb_launch_count(uint64_t *count);
 

@@ -226,3 +226,17 @@ def test_pair_ops_against_oracle(gms, orc, seed):
     assert np.allclose(got[finite], ref_[finite], rtol=1e-13, atol=0)
     with pytest.raises(gms.GmsbError):
         g.intersect_count_batch(np.array([0, g.n], np.int32), np.array([0, 0], np.int32))
+
+
+def test_orientation_fallback_path(gms, orc, monkeypatch):
+    """Lists longer than the on-chip sorter take the global radix-sort path; force it with a tiny cap."""
+    s, d = random_graph_edges(77, 3000, 80000, skew=1.2)
+    o = orc.from_el(s, d, True)
+    want = o.tc_total()
+    for cap in ("0", "40", "8192"):
+        monkeypatch.setenv("GMSB_ORIENT_SORT_CAP", cap)
+        g = gms.Graph.from_edgelist(s, d, True)
+        assert g.tc_total_ex()[0] == want, cap
+        rank = o.degree_order(True)
+        dag, odag = g.orient(rank), o.induce_directed(rank)
+        assert same_csr(dag.export_csr(), odag.csr()), cap
