@@ -42,6 +42,16 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# Libraries (NCCL's version banner, the reference's progress lines) write to fd 1; the contract is ONE JSON line on
+# stdout, so fd 1 is pointed at stderr for the whole run and the result line goes to the saved descriptor.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit_result(obj):
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -128,15 +138,15 @@ def run_reference(args):
     value = edges / T
     sample = (f"every {stride}-th undirected edge (u<v, CSR order) of kronecker-{args.scale} per step, "
               f"SortedSet::intersect_count over full neighbourhoods, omp dynamic, {cores} threads")
-    print(json.dumps({
+    emit_result({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * T / max(args.steps, 1),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
         "config": {"workload": f"triangle counting, Kronecker scale-{args.scale} edge factor 16 (n={g.n}, m={m})",
                    "sample": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    })
 
 
 def run_ours(args):
@@ -299,8 +309,11 @@ def run_ours(args):
         except Exception as ex:      # the baseline is reported, never required
             out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(ex)}
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        emit_result(out)
     g.free()
+    gd.barrier()
+    if torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()
 
 
 def main():
