@@ -105,10 +105,13 @@ def cpu_sample_stride(deg, cores, target_seconds):
 def cpu_lib():
     from oracle import binding
     ref = binding.reference()
-    if ref is not None:
-        return ref, "reference"
-    binding.build()
-    return binding.oracle(), "port"
+    lib, kind = (ref, "reference") if ref is not None else (None, "port")
+    if lib is None:
+        binding.build()
+        lib = binding.oracle()
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU baseline is meant to use every host core
+    lib.set_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+    return lib, kind
 
 
 def run_reference(args):

@@ -175,12 +175,50 @@ k_emit_sorted(const eid_t *__restrict__ off, const vid_t *__restrict__ rnbr, int
             v = warp_bitonic_sort(v, lane);
             if (lane < c) dnbr[ob + lane] = v;
         } else if (lane == 0) {
-            big[atomicAdd(nbig, 1)] = ru;
+            // two queues filled from opposite ends of one array: [0, nbig[0]) mid-size lists, (n-1-nbig[1], n-1] long
+            if (c <= 512) big[atomicAdd(&nbig[0], 1)] = ru;
+            else big[n - 1 - atomicAdd(&nbig[1], 1)] = ru;
         }
     }
 }
 
-// (3) CTA sorter for the queued lists: bitonic network in shared memory, sized per list.
+// (3a) warp sorter for queued lists of 33..kWarpSortCap elements: one warp per list, bitonic network in the warp's
+// own shared-memory slice (no block barriers), eight lists per CTA in flight.
+constexpr int kWarpSortCap = 512;
+__global__ void __launch_bounds__(256)
+k_sort_mid(const vid_t *__restrict__ big, int nbig, const eid_t *__restrict__ doff, vid_t *__restrict__ dnbr) {
+    __shared__ vid_t bufs[8][kWarpSortCap];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    vid_t *buf = bufs[wib];
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < nbig; t += nwarps) {
+        const vid_t ru = big[t];
+        const eid_t ob = doff[ru];
+        const int c = (int)(doff[ru + 1] - ob);
+        if (c > kWarpSortCap) continue;                    // left to the CTA sorter
+        int P = 64;
+        while (P < c) P <<= 1;
+        __syncwarp();
+        for (int i = lane; i < P; i += 32) buf[i] = i < c ? dnbr[ob + i] : 0x7fffffff;
+        __syncwarp();
+        for (int k = 2; k <= P; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int q = lane; q < (P >> 1); q += 32) {
+                    // q-th compare-exchange pair of this step: insert a zero bit at position log2(j)
+                    const int i = ((q & ~(j - 1)) << 1) | (q & (j - 1));
+                    const int x = i | j;
+                    const vid_t a = buf[i], bq = buf[x];
+                    const bool up = (i & k) == 0;
+                    if ((a > bq) == up) { buf[i] = bq; buf[x] = a; }
+                }
+                __syncwarp();
+            }
+        }
+        for (int i = lane; i < c; i += 32) dnbr[ob + i] = buf[i];
+    }
+}
+
+// (3b) CTA sorter for the few longer lists: bitonic network in shared memory, sized per list.
 constexpr int kSortCap = 8192;
 __global__ void __launch_bounds__(256)
 k_sort_big(const vid_t *__restrict__ big, int nbig, const eid_t *__restrict__ doff, vid_t *__restrict__ dnbr) {
@@ -189,6 +227,7 @@ k_sort_big(const vid_t *__restrict__ big, int nbig, const eid_t *__restrict__ do
         const vid_t ru = big[t];
         const eid_t ob = doff[ru];
         const int c = (int)(doff[ru + 1] - ob);
+        if (c <= kWarpSortCap) continue;                   // done by the warp sorter
         int P = 64;
         while (P < c) P <<= 1;
         __syncthreads();
@@ -253,18 +292,25 @@ void orient_by_rank(const Graph &g, const vid_t *rank_dev, DevBuf<eid_t> &doff, 
     if (const char *env = getenv("GMSB_ORIENT_SORT_CAP")) cap = std::min(kSortCap, std::max(0, atoi(env)));   // tests
     if (maxd <= cap) {
         // lists sorted on chip: registers (<= 32) or shared memory; one streaming pass in, one out
+        static_assert(kWarpSortCap == 512, "k_emit_sorted splits its queues at 512");
         DevBuf<vid_t> big(n);
-        DevBuf<int> nbig(1);
+        DevBuf<int> nbig(2);
         nbig.zero();
         k_emit_sorted<<<grid_for(n * 32, 256), 256, 0, r.stream>>>(g.off.p, rnbr.p, n, rank_dev, doff.p, dnbr.p, big.p,
                                                                   nbig.p);
         launched();
-        const int nb = nbig.get(0);
-        if (nb) {
+        int h_nb[2];
+        nbig.download(h_nb, 2);
+        if (h_nb[0]) {
+            const int grid = (int)std::min<int64_t>(ceil_div(h_nb[0], 8), (int64_t)r.sm_count * 12);
+            k_sort_mid<<<grid, 256, 0, r.stream>>>(big.p, h_nb[0], doff.p, dnbr.p); launched();
+        }
+        if (h_nb[1]) {
             int P = 64;
             while (P < maxd) P <<= 1;
-            const int grid = (int)std::min<int64_t>(nb, (int64_t)r.sm_count * 16);
-            k_sort_big<<<grid, 256, (size_t)P * sizeof(vid_t), r.stream>>>(big.p, nb, doff.p, dnbr.p); launched();
+            const int grid = (int)std::min<int64_t>(h_nb[1], (int64_t)r.sm_count * 8);
+            k_sort_big<<<grid, 256, (size_t)P * sizeof(vid_t), r.stream>>>(big.p + (n - h_nb[1]), h_nb[1], doff.p, dnbr.p);
+            launched();
         }
     } else {
         // general fallback for lists longer than the on-chip sorter: one global radix sort of (rank[u], rank[v]) keys
