@@ -154,13 +154,18 @@ __global__ void k_fill_items(int64_t n, const uint32_t *__restrict__ keys, const
 // Order key of an item: L2 tile of its first suffix (tile-major order keeps the lists that concurrently running
 // CTAs stream inside the L2), then heaviest vertex first.
 __global__ void k_item_keys(const Item *__restrict__ items, int64_t cnt, const uint64_t *__restrict__ desc, int64_t n,
-                            int tile_shift, uint64_t *__restrict__ keys) {
+                            int tile_shift, const eid_t *__restrict__ off, const vid_t *__restrict__ nbr,
+                            uint64_t *__restrict__ keys, unsigned long long *__restrict__ n_small,
+                            int *__restrict__ small_words) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < cnt; i += (int64_t)gridDim.x * blockDim.x) {
         const Item it = items[i];
         // a slice that mixes classes has no single u-range: use its longest-suffix part (the bulk of its work)
         const int64_t d = it.begin + (it.n1 < it.count ? it.n1 : (it.n0 < it.count ? it.n0 : 0));
         const uint64_t tile = tile_shift > 0 ? (desc[d] >> kLenBits) >> tile_shift : 0;
-        keys[i] = (tile << 32) | (uint64_t)(uint32_t)(n - 1 - it.v);
+        const int words = (int)(((int64_t)nbr[off[it.v + 1] - 1] - it.v + 31) >> 5);
+        const bool wide = (words + 1) * 4 > kSmallWindowBytes;
+        if (!wide) { atomicAdd(n_small, 1ull); atomicMax(small_words, words); }
+        keys[i] = ((uint64_t)wide << 63) | (tile << 32) | (uint64_t)(uint32_t)(n - 1 - it.v);
     }
 }
 
@@ -201,7 +206,7 @@ __global__ void k_compact_light(const uint32_t *__restrict__ keys, const uint64_
 constexpr int kDescChunk = 4;
 
 // G lanes cooperate on one descriptor; the warp takes 32/G descriptors per ticket (4 when G == 32).
-template <int G>
+template <int G, bool DEEP = false>
 __device__ __forceinline__ uint32_t stream_class(const uint64_t *__restrict__ dptr, int lo, int hi, int *ticket,
                                                  const vid_t *__restrict__ nbr, const uint32_t *bm, uint32_t base,
                                                  uint32_t cap_words, int lane) {
@@ -220,13 +225,23 @@ __device__ __forceinline__ uint32_t stream_class(const uint64_t *__restrict__ dp
                 const uint64_t ds = __shfl_sync(0xffffffffu, mine, k);
                 const vid_t *__restrict__ p = nbr + (ds >> kLenBits);
                 const int len = (int)(ds & kLenMask);
-                for (int j = lane; j < len; j += 128) {
-                    const uint32_t x0 = (uint32_t)p[j] - base;
-                    const uint32_t x1 = j + 32 < len ? (uint32_t)p[j + 32] - base : ~0u;
-                    const uint32_t x2 = j + 64 < len ? (uint32_t)p[j + 64] - base : ~0u;
-                    const uint32_t x3 = j + 96 < len ? (uint32_t)p[j + 96] - base : ~0u;
-                    hits += probe(bm, x0, cap_words) + probe(bm, x1, cap_words) + probe(bm, x2, cap_words) +
-                            probe(bm, x3, cap_words);
+                if constexpr (DEEP) {
+                    for (int j = lane; j < len; j += 256) {       // 8 loads in flight per lane
+                        uint32_t x[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) x[q] = j + 32 * q < len ? (uint32_t)p[j + 32 * q] - base : ~0u;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) hits += probe(bm, x[q], cap_words);
+                    }
+                } else {
+                    for (int j = lane; j < len; j += 128) {
+                        const uint32_t x0 = (uint32_t)p[j] - base;
+                        const uint32_t x1 = j + 32 < len ? (uint32_t)p[j + 32] - base : ~0u;
+                        const uint32_t x2 = j + 64 < len ? (uint32_t)p[j + 64] - base : ~0u;
+                        const uint32_t x3 = j + 96 < len ? (uint32_t)p[j + 96] - base : ~0u;
+                        hits += probe(bm, x0, cap_words) + probe(bm, x1, cap_words) + probe(bm, x2, cap_words) +
+                                probe(bm, x3, cap_words);
+                    }
                 }
             }
         } else {
@@ -253,7 +268,7 @@ __device__ __forceinline__ uint32_t stream_class(const uint64_t *__restrict__ dp
     return hits;
 }
 
-template <int BLOCK, int MINB>
+template <int BLOCK, int MINB, bool DEEP = false>
 __global__ void __launch_bounds__(BLOCK, MINB)
 k_tc_bitmap(const Item *__restrict__ items, int64_t first, int64_t stride, int64_t count, uint32_t cap_words,
             const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, const uint64_t *__restrict__ desc,
@@ -280,7 +295,7 @@ k_tc_bitmap(const Item *__restrict__ items, int64_t first, int64_t stride, int64
         }
         __syncthreads();                              // bitmap of N+(v) complete
         const uint64_t *__restrict__ dptr = desc + item.begin;
-        uint32_t hits = stream_class<32>(dptr, item.n1, item.count, &s_next[2], nbr, bm, base, cap_words, lane);
+        uint32_t hits = stream_class<32, DEEP>(dptr, item.n1, item.count, &s_next[2], nbr, bm, base, cap_words, lane);
         hits += stream_class<8>(dptr, item.n0, item.n1, &s_next[1], nbr, bm, base, cap_words, lane);
         hits += stream_class<1>(dptr, 0, item.n0, &s_next[0], nbr, bm, base, cap_words, lane);
         hits64 += hits;
@@ -409,9 +424,14 @@ TcPlan *build_plan(const Dag &d, const gmsb_tc_options &opt) {
             DevBuf<uint64_t> ik(p->n_items), ik2(p->n_items);
             DevBuf<Item> items2(p->n_items);
             const int tile_shift = opt.reserved[1] > 0 ? opt.reserved[1] : (opt.reserved[1] < 0 ? 0 : 24);
+            DevBuf<unsigned long long> nsm(1);
+            DevBuf<int> smw(1);
+            nsm.zero(); smw.zero();
             k_item_keys<<<grid_for(p->n_items, 256), 256, 0, r.stream>>>(p->items.p, p->n_items, p->sorted_vals, n,
-                                                                        tile_shift, ik.p);
+                                                                        tile_shift, d.off.p, d.nbr.p, ik.p, nsm.p, smw.p);
             launched();
+            p->n_items_small = (int64_t)nsm.get(0);
+            p->small_span_words = smw.get(0);
             size_t bytes = 0;
             GMSB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, ik.p, ik2.p, p->items.p, items2.p, p->n_items, 0,
                                                       64, r.stream));
@@ -493,26 +513,37 @@ void tc_total(Graph &g, const gmsb_tc_options &opt_in, uint64_t *out, gmsb_tc_st
 
     t_bm.start();
     if (my_items) {
-        // CTA shape: 512 threads x 3 resident CTAs by default; reserved[2] picks another shape for experiments
-        int BLOCK = 512;
-        auto kern = k_tc_bitmap<512, 3>;
-        if (opt.reserved[2] == 1) { BLOCK = 256; kern = k_tc_bitmap<256, 6>; }
-        else if (opt.reserved[2] == 2) { BLOCK = 1024; kern = k_tc_bitmap<1024, 1>; }
-        else if (opt.reserved[2] == 3) { BLOCK = 512; kern = k_tc_bitmap<512, 4>; }
-        else if (opt.reserved[2] == 4) { BLOCK = 256; kern = k_tc_bitmap<256, 8>; }
-        const size_t smem = ((size_t)p.max_span_words + 1) * 4;
-        if (smem > 48 * 1024)
-            GMSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int resident = 0;
-        GMSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, BLOCK, smem));
-        GMSB_REQUIRE(resident >= 1, "tc: bitmap kernel does not fit on an SM");
-        GMSB_REQUIRE(my_items < (int64_t(1) << 31), "tc: too many bitmap items");
-        const int grid = (int)std::min<int64_t>(my_items, (int64_t)r.sm_count * resident);   // one persistent wave
-        DevBuf<unsigned int> ticket(1);
-        ticket.zero();
-        kern<<<grid, BLOCK, smem, r.stream>>>(p.items.p, pi, P, my_items, (uint32_t)p.max_span_words, d.off.p, d.nbr.p,
-                                              p.sorted_vals, total.p, ticket.p);
-        launched();                                        // (ticket's free is stream-ordered after the kernel)
+        GMSB_REQUIRE(p.n_items < (int64_t(1) << 31), "tc: too many bitmap items");
+        DevBuf<unsigned int> tickets(2);
+        tickets.zero();
+        // one persistent wave per window class (the ticket's free is stream-ordered after the kernels)
+        auto launch = [&](auto kern, int BLOCK, const Item *items, int64_t cnt, int cap_words, unsigned int *ticket) {
+            const int64_t mine = part_size(cnt, pi, P);
+            if (mine == 0) return;
+            const size_t smem = ((size_t)cap_words + 1) * 4;
+            if (smem > 48 * 1024)
+                GMSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int resident = 0;
+            GMSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, BLOCK, smem));
+            GMSB_REQUIRE(resident >= 1, "tc: bitmap kernel does not fit on an SM");
+            const int grid = (int)std::min<int64_t>(mine, (int64_t)r.sm_count * resident);
+            kern<<<grid, BLOCK, smem, r.stream>>>(items, pi, P, mine, (uint32_t)cap_words, d.off.p, d.nbr.p,
+                                                  p.sorted_vals, total.p, ticket);
+            launched();
+        };
+        const int shape = opt.reserved[2];              // experiments: one launch with another CTA shape
+        if (shape == 0) {
+            // small windows (<= 55 KB of bitmap): four CTAs of 512 threads per SM = 64 resident warps
+            launch(k_tc_bitmap<512, 4>, 512, p.items.p, p.n_items_small, p.small_span_words, tickets.p);
+            // wide windows: three CTAs per SM
+            launch(k_tc_bitmap<512, 3>, 512, p.items.p + p.n_items_small, p.n_items - p.n_items_small,
+                   p.max_span_words, tickets.p + 1);
+        } else if (shape == 1) launch(k_tc_bitmap<256, 6>, 256, p.items.p, p.n_items, p.max_span_words, tickets.p);
+        else if (shape == 2) launch(k_tc_bitmap<1024, 1>, 1024, p.items.p, p.n_items, p.max_span_words, tickets.p);
+        else if (shape == 3) launch(k_tc_bitmap<512, 4>, 512, p.items.p, p.n_items, p.max_span_words, tickets.p);
+        else if (shape == 4) launch(k_tc_bitmap<256, 8>, 256, p.items.p, p.n_items, p.max_span_words, tickets.p);
+        else if (shape == 5) launch(k_tc_bitmap<512, 3, true>, 512, p.items.p, p.n_items, p.max_span_words, tickets.p);
+        else launch(k_tc_bitmap<512, 3>, 512, p.items.p, p.n_items, p.max_span_words, tickets.p);
     }
     t_bm.stop();
     t_mg.start();

@@ -14,6 +14,8 @@ constexpr int kShortLen = 8;                        // class 0: len <= 8   -> on
 constexpr int kMidLen = 96;                         // class 1: len <= 96  -> eight lanes per descriptor
                                                     // class 2: longer     -> one warp per descriptor
 
+constexpr int kSmallWindowBytes = 55000;            // 4 x (55 KB bitmap + static) <= 227 KB per SM
+
 struct Item {            // one CTA work unit: a slice of hub v's incoming descriptors
     int32_t v;
     int32_t count;       // descriptors in the slice
@@ -27,6 +29,10 @@ struct TcPlan {
     DevBuf<Item> items;                 // bitmap work items
     int64_t n_items = 0;
     int max_span_words = 0;
+    // items are ordered small-window first: [0, n_items_small) fit kSmallWindowBytes of bitmap, which lets four
+    // CTAs share an SM (64 resident warps); the few wide-window hubs run in a second launch with three
+    int64_t n_items_small = 0;
+    int small_span_words = 0;
     DevBuf<uint64_t> m_desc, g_desc;    // light edges for merge / gallop
     DevBuf<vid_t> m_v, g_v;
     int64_t n_merge = 0, n_gallop = 0, n_bitmap_edges = 0;

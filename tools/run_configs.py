@@ -55,9 +55,10 @@ def main():
         if 3 in cfgs:
             prev = None
             for k in range(3, args.kmax + 1):
-                if prev is not None and prev * 12 > args.kcap_seconds:
+                if prev is not None and prev * 50 > args.kcap_seconds:
                     emit(config="cfg3-kclique", scale=args.scale22, k=k, skipped=f"predicted > {args.kcap_seconds}s "
-                         f"(previous k took {prev:.1f}s; cost grows ~10x per k)")
+                         f"(previous k took {prev:.1f}s; cost grew ~50x from k=5 to k=6 at scale 22)")
+                    prev = prev * 50
                     continue
                 t0 = time.time()
                 c = g.kclique_count(k)

@@ -1,4 +1,11 @@
-"""Turn the raw captures in gpurun_out/ into the tracked summaries under profiles/ (per round tag)."""
+"""Turn the raw captures in gpurun_out/ into the tracked summaries under profiles/ (per round tag).
+
+    python tools/summarise_profiles.py <tag>
+
+Inputs (written by tools/gpu_profile.sh on the GPU box): launches_<tag>.csv, prof_tc_<tag>.ncu-rep,
+bench_<tag>.json, sweep_variants_<tag>.jsonl.  Outputs: profiles/<tag>_*.{csv,txt,json,jsonl} and
+profiles/traffic.json (DRAM bytes per launch of each triangle kernel; bench.py's roofline.traffic reads it).
+"""
 import collections
 import csv
 import json
@@ -11,14 +18,17 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 import ncu_summary  # noqa: E402
 
 
+def to_ms(value, unit):
+    v = float(value.replace(",", ""))
+    return v / 1e6 if unit.startswith("n") else (v / 1e3 if unit.startswith("u") else v)
+
+
 def launch_list(tag, out):
     path = os.path.join(ROOT, "gpurun_out", f"launches_{tag}.csv")
     lines = [ln for ln in open(path) if not ln.startswith("==")]
     agg, total = collections.OrderedDict(), 0.0
     for row in csv.DictReader(lines):
-        v = float(row["Metric Value"].replace(",", ""))
-        unit = row["Metric Unit"]
-        ms = v / 1e6 if unit.startswith("n") else (v / 1e3 if unit.startswith("u") else v)
+        ms = to_ms(row["Metric Value"], row["Metric Unit"])
         a = agg.setdefault(row["Kernel Name"][:90], [0, 0.0])
         a[0] += 1
         a[1] += ms
@@ -32,6 +42,27 @@ def launch_list(tag, out):
             f.write(f"{t:.3f},{c},{t / c:.3f},{t / total:.4f},{k}\n")
 
 
+def traffic(rep, tag):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    kn, rd, wr, du = (hdr.index(x) for x in ("Kernel Name", "dram__bytes_read.sum", "dram__bytes_write.sum",
+                                             "gpu__time_duration.sum"))
+    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}
+    out = {}
+    for r in rows[2:]:
+        for name in ("k_tc_bitmap", "k_tc_merge", "k_tc_gallop"):
+            if name in r[kn] and name not in out:
+                try:
+                    b = float(r[rd]) * scale[units[rd]] + float(r[wr]) * scale[units[wr]]
+                except (ValueError, KeyError):
+                    continue
+                out[name] = {"dram_bytes_per_launch": b, "ncu_duration_ms": to_ms(r[du], units[du]),
+                             "capture": f"profiles/{tag}_tc_kernels_ncu.txt", "workload": "kronecker-24, one GPU"}
+    with open(os.path.join(ROOT, "profiles", "traffic.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+
 def main(tag):
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     launch_list(tag, os.path.join(ROOT, "profiles", f"{tag}_launches.csv"))
@@ -41,7 +72,8 @@ def main(tag):
         print(f"# ncu --set full --clock-control none -k regex:k_tc_(bitmap|merge|gallop) -s 3 -c 3, scale 24, tag {tag}")
         ncu_summary.main(rep)
         sys.stdout = sys.__stdout__
-    for name in (f"bench_{tag}.json", f"sweep_variants_{tag}.jsonl"):
+    traffic(rep, tag)
+    for name in (f"bench_{tag}.json", f"sweep_variants_{tag}.jsonl", f"configs_{tag}.jsonl"):
         src = os.path.join(ROOT, "gpurun_out", name)
         if os.path.exists(src):
             with open(src) as fi, open(os.path.join(ROOT, "profiles", f"{tag}_{name.replace('_' + tag, '')}"), "w") as fo:
