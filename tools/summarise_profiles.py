@@ -52,13 +52,18 @@ def traffic(rep, tag):
     out = {}
     for r in rows[2:]:
         for name in ("k_tc_bitmap", "k_tc_merge", "k_tc_gallop"):
-            if name in r[kn] and name not in out:
+            if name in r[kn]:
                 try:
                     b = float(r[rd]) * scale[units[rd]] + float(r[wr]) * scale[units[wr]]
                 except (ValueError, KeyError):
                     continue
-                out[name] = {"dram_bytes_per_launch": b, "ncu_duration_ms": to_ms(r[du], units[du]),
-                             "capture": f"profiles/{tag}_tc_kernels_ncu.txt", "workload": "kronecker-24, one GPU"}
+                # the capture holds ONE counting step; the bitmap kernel runs as two launches (small / wide windows)
+                e = out.setdefault(name, {"dram_bytes_per_launch": 0.0, "ncu_duration_ms": 0.0, "launches_summed": 0,
+                                          "capture": f"profiles/{tag}_tc_kernels_ncu.txt",
+                                          "workload": "kronecker-24, one GPU, one counting step"})
+                e["dram_bytes_per_launch"] += b
+                e["ncu_duration_ms"] += to_ms(r[du], units[du])
+                e["launches_summed"] += 1
     with open(os.path.join(ROOT, "profiles", "traffic.json"), "w") as f:
         json.dump(out, f, indent=1)
 
@@ -73,6 +78,14 @@ def main(tag):
         ncu_summary.main(rep)
         sys.stdout = sys.__stdout__
     traffic(rep, tag)
+    forced = os.path.join(ROOT, "gpurun_out", f"prof_forced_{tag}.ncu-rep")
+    if os.path.exists(forced):
+        with open(os.path.join(ROOT, "profiles", f"{tag}_forced_variants_ncu.txt"), "w") as f:
+            sys.stdout = f
+            print(f"# ncu --set full, scale 22, every oriented edge forced through ONE light kernel "
+                  f"(variant=merge, then variant=gallop); tag {tag}")
+            ncu_summary.main(forced)
+            sys.stdout = sys.__stdout__
     for name in (f"bench_{tag}.json", f"sweep_variants_{tag}.jsonl", f"configs_{tag}.jsonl"):
         src = os.path.join(ROOT, "gpurun_out", name)
         if os.path.exists(src):
