@@ -179,7 +179,9 @@ class CpuLib:
                                     C.POINTER(C.c_int64)]),
             })
         else:
-            sig.update({"degeneracy_danisch_heap": (None, [C.c_void_p, _i32p])})
+            sig.update({"degeneracy_danisch_heap": (None, [C.c_void_p, _i32p]),
+                        "load_file": (C.c_void_p, [C.c_char_p, C.c_int]),
+                        "write_file": (None, [C.c_void_p, C.c_char_p, C.c_int])})
         self._fn = {}
         for name, (res, args) in sig.items():
             f = getattr(self.dll, prefix + name)
@@ -255,6 +257,13 @@ class CpuLib:
     def contains(self, a, x):
         a, na = self._arr(a)
         return bool(self._f("contains")(a, na, x))
+
+    # --- reference-only: graph files through the reference's own reader / writer
+    def load_file(self, path, symmetrize=True):
+        return Graph(self, self._f("load_file")(path.encode(), int(symmetrize)))
+
+    def write_file(self, g, path, serialized=True):
+        self._f("write_file")(g.h, path.encode(), int(serialized))
 
     # --- oracle-only
     def degeneracy_rank(self, g):

@@ -165,6 +165,23 @@ void gmsref_export_csr(void *h, int64_t *off, int32_t *nbr) {
     off[n] = pos;
 }
 
+// ---- graph files (gapbs reader.h / writer.h through Builder::MakeGraph and WriterBase::WriteGraph) -------------------------
+void *gmsref_load_file(const char *path, int symmetrize) {
+    Quiet q;
+    GMS::CLI::Args args;
+    args.graph_spec.is_generator = false;
+    args.graph_spec.name = path;
+    args.symmetrize = symmetrize != 0;
+    auto *h = new RefGraph();
+    h->g = args.load_graph();
+    return h;
+}
+void gmsref_write_file(void *h, const char *path, int serialized) {
+    Quiet q;
+    WriterBase<NodeId> w(static_cast<RefGraph *>(h)->g);
+    w.WriteGraph(path, serialized != 0);
+}
+
 int gmsref_worth_relabelling(void *h) { return WorthRelabelling(static_cast<RefGraph *>(h)->g) ? 1 : 0; }
 
 void *gmsref_relabel_by_degree(void *h) {
