@@ -220,7 +220,7 @@ __device__ __forceinline__ uint32_t stream_class(const uint64_t *__restrict__ dp
         if (d0 >= hi) break;
         if constexpr (G == 32) {
             const int nd = min(BATCH, hi - d0);
-            const uint64_t mine = lane < nd ? dptr[d0 + lane] : 0ull;
+            const uint64_t mine = lane < nd ? __ldcs(&dptr[d0 + lane]) : 0ull;
             for (int k = 0; k < nd; ++k) {
                 const uint64_t ds = __shfl_sync(0xffffffffu, mine, k);
                 const vid_t *__restrict__ p = nbr + (ds >> kLenBits);
@@ -246,7 +246,7 @@ __device__ __forceinline__ uint32_t stream_class(const uint64_t *__restrict__ dp
             }
         } else {
             const int idx = d0 + lane / G, sub = lane % G;
-            const uint64_t ds = idx < hi ? dptr[idx] : 0ull;
+            const uint64_t ds = idx < hi ? __ldcs(&dptr[idx]) : 0ull;
             const vid_t *__restrict__ p = nbr + (ds >> kLenBits);
             const int len = (int)(ds & kLenMask);
             if constexpr (G == 1) {
