@@ -71,6 +71,8 @@ SIGNATURES = {
     "gmsb_graph_free": (C.c_int, [C.c_void_p]),
     "gmsb_order_degree": (C.c_int, [C.c_void_p, C.c_int, _i32p]),
     "gmsb_order_degeneracy": (C.c_int, [C.c_void_p, _i32p]),
+    "gmsb_order_degeneracy_approx": (C.c_int, [C.c_void_p, C.c_double, C.c_int, _i32p]),
+    "gmsb_graph_worth_relabelling": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "gmsb_orient": (C.c_int, [C.c_void_p, _i32p, C.POINTER(C.c_void_p)]),
     "gmsb_tc_total": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "gmsb_tc_total_ex": (C.c_int, [C.c_void_p, C.POINTER(TcOptions), C.POINTER(C.c_uint64), C.POINTER(TcStats)]),
@@ -237,6 +239,16 @@ class Graph:
         out = np.zeros(max(self.n, 1), np.int32)
         _check(lib().gmsb_order_degeneracy(self.h, out))
         return out[:self.n]
+
+    def degeneracy_order_approx(self, epsilon=1.0, rank_format=False):
+        out = np.zeros(max(self.n, 1), np.int32)
+        _check(lib().gmsb_order_degeneracy_approx(self.h, float(epsilon), int(rank_format), out))
+        return out[:self.n]
+
+    def worth_relabelling(self):
+        v = C.c_int(0)
+        _check(lib().gmsb_graph_worth_relabelling(self.h, C.byref(v)))
+        return bool(v.value)
 
     def orient(self, ranking):
         h = C.c_void_p()

@@ -4,8 +4,10 @@
 #include "orient.cuh"
 #include "ops.cuh"
 
+#include <algorithm>
 #include <cstring>
 #include <mutex>
+#include <random>
 #include <unordered_map>
 #include <vector>
 
@@ -246,6 +248,39 @@ GMSB_API int gmsb_order_degeneracy(gmsb_graph_t g, int32_t *out_rank) {
         Graph &gr = G(g);
         GMSB_REQUIRE(out_rank || gr.n == 0, "null output");
         degeneracy_rank(gr, out_rank);
+    });
+}
+GMSB_API int gmsb_order_degeneracy_approx(gmsb_graph_t g, double epsilon, int rank_format, int32_t *out) {
+    return guarded([&] {
+        Graph &gr = G(g);
+        GMSB_REQUIRE(out || gr.n == 0, "null output");
+        degeneracy_order_approx(gr, epsilon, rank_format != 0, out);
+    });
+}
+GMSB_API int gmsb_graph_worth_relabelling(gmsb_graph_t g, int *out) {
+    return guarded([&] {
+        Graph &gr = G(g);
+        GMSB_REQUIRE(out, "null output");
+        // host-side heuristic on the degree array (gapbs/benchmark.h:158-176); same libstdc++ RNG stream as the reference
+        *out = 0;
+        const int64_t n = gr.n;
+        if (n == 0 || (gr.slots / 2) / n < 10) return;
+        std::vector<eid_t> off(n + 1);
+        gr.off.download(off.data(), n + 1);
+        std::mt19937 rng(27491095);
+        std::uniform_int_distribution<vid_t> pick(0, (vid_t)(n - 1));
+        const int64_t ns = std::min<int64_t>(1000, n);
+        std::vector<int64_t> s(ns);
+        int64_t total = 0;
+        for (int64_t t = 0; t < ns; ++t) {
+            vid_t v;
+            do { v = pick(rng); } while (off[v + 1] == off[v]);
+            s[t] = off[v + 1] - off[v];
+            total += s[t];
+        }
+        std::sort(s.begin(), s.end());
+        const double avg = static_cast<double>(total) / ns, med = static_cast<double>(s[ns / 2]);
+        *out = avg / 1.3 > med ? 1 : 0;
     });
 }
 GMSB_API int gmsb_orient(gmsb_graph_t g, const int32_t *ranking, gmsb_graph_t *dag) {

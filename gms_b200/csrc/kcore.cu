@@ -9,6 +9,7 @@
 // (verifiers/degeneracy_verifier.h:69-85: every vertex has at most `degeneracy` neighbours that are removed after
 // it), in the reference's ranking convention: the r-th removed vertex (r = 1..n) gets rank n - r.
 #include "common.cuh"
+#include "sort.cuh"
 #include "isect.cuh"
 #include "ops.cuh"
 
@@ -89,6 +90,84 @@ void degeneracy_rank(Graph &g, vid_t *out_rank) {
         }
     }
     rank.download(out_rank, n);
+}
+
+// ---- approximate degeneracy order (ADG) ---------------------------------------------------------------------------------
+// Replaces  PpParallel::getDegeneracyOrderingApproxCGraph<boundary_function::averageDegree, useRankFormat>
+//           gms/algorithms/preprocessing/parallel/degeneracy_approx_csr.h:13-78, boundary_function.h:15-25
+// Every round removes ALL vertices whose residual degree is <= (1+eps) * average residual degree, ordered inside the
+// round by that degree (ties by id here; the reference's parallel partition + sort leave ties unspecified), and
+// decrements the degrees of their neighbours.  O(log n) rounds; a (2+2eps)-approximation of the degeneracy order.
+namespace {
+__global__ void k_live_degree_sum(int64_t n, const int *__restrict__ deg, const int *__restrict__ gone,
+                                  unsigned long long *__restrict__ acc /* [0]=sum [1]=count */) {
+    unsigned long long s = 0, c = 0;
+    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x)
+        if (!gone[v]) { s += (unsigned long long)deg[v]; c++; }
+    s = warp_sum(s); c = warp_sum(c);
+    if ((threadIdx.x & 31) == 0 && c) { atomicAdd(&acc[0], s); atomicAdd(&acc[1], c); }
+}
+__global__ void k_collect_keys(int64_t n, unsigned int border, const int *__restrict__ deg, int *__restrict__ gone,
+                               uint64_t *__restrict__ keys, int *__restrict__ qsize) {
+    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x)
+        if (!gone[v] && (long long)deg[v] <= (long long)border) {
+            gone[v] = 1;
+            keys[atomicAdd(qsize, 1)] = ((uint64_t)(uint32_t)deg[v] << 32) | (uint32_t)v;
+        }
+}
+__global__ void k_adg_assign(const uint64_t *__restrict__ sorted, int qs, int64_t done, int rank_format,
+                             vid_t *__restrict__ out, vid_t *__restrict__ queue) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < qs; i += gridDim.x * blockDim.x) {
+        const vid_t v = (vid_t)(uint32_t)sorted[i];
+        queue[i] = v;
+        if (rank_format) out[v] = (vid_t)(done + i); else out[done + i] = v;
+    }
+}
+// PUSH-style update: every neighbour's counter drops, removed or not (degeneracy_approx_csr.h:62-66)
+__global__ void k_adg_relax(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, const vid_t *__restrict__ queue,
+                            int qs, int *__restrict__ deg) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = warp; i < qs; i += nwarps) {
+        const vid_t v = queue[i];
+        for (eid_t e = off[v] + lane; e < off[v + 1]; e += 32) atomicSub(&deg[nbr[e]], 1);
+    }
+}
+}  // namespace
+
+void degeneracy_order_approx(Graph &g, double epsilon, bool rank_format, vid_t *out_host) {
+    GMSB_REQUIRE(!g.directed, "order_degeneracy_approx: graph must be undirected");
+    GMSB_REQUIRE(epsilon >= 0, "order_degeneracy_approx: epsilon must be non-negative");
+    Runtime &r = rt();
+    const int64_t n = g.n;
+    if (n == 0) return;
+    GMSB_REQUIRE(n < (int64_t(1) << 31), "order_degeneracy_approx: too many vertices");
+    DevBuf<int> deg(n), gone(n), qsize(1);
+    DevBuf<vid_t> out(n), queue(n);
+    DevBuf<uint64_t> keys(n), alt(n);
+    DevBuf<unsigned long long> acc(2);
+    gone.zero();
+    k_init_degrees<<<grid_for(n, 256), 256, 0, r.stream>>>(g.off.p, n, deg.p); launched();
+    int64_t done = 0;
+    while (done < n) {
+        acc.zero(); qsize.zero();
+        k_live_degree_sum<<<grid_for(n, 256), 256, 0, r.stream>>>(n, deg.p, gone.p, acc.p); launched();
+        unsigned long long h[2];
+        acc.download(h, 2);
+        const double res = (double)(long long)h[0];
+        const unsigned int border = (unsigned int)((1 + epsilon) * (res / (double)h[1]));   // boundary_function.h:24
+        k_collect_keys<<<grid_for(n, 256), 256, 0, r.stream>>>(n, border, deg.p, gone.p, keys.p, qsize.p); launched();
+        const int qs = qsize.get(0);
+        GMSB_REQUIRE(qs > 0, "order_degeneracy_approx: no progress");
+        uint64_t *sorted = radix_sort_keys(keys.p, alt.p, qs, 0, 64);
+        k_adg_assign<<<grid_for(qs, 256), 256, 0, r.stream>>>(sorted, qs, done, rank_format ? 1 : 0, out.p, queue.p);
+        launched();
+        k_adg_relax<<<grid_for((int64_t)qs * 32, 256), 256, 0, r.stream>>>(g.off.p, g.nbr.p, queue.p, qs, deg.p);
+        launched();
+        done += qs;
+    }
+    out.download(out_host, n);
 }
 
 }  // namespace gmsb

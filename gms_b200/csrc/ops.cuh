@@ -21,6 +21,7 @@ void edge_scores_from_support(Graph &g, int metric, const int64_t *base_dev, dou
 
 // kcore.cu
 void degeneracy_rank(Graph &g, vid_t *out_rank);
+void degeneracy_order_approx(Graph &g, double epsilon, bool rank_format, vid_t *out_host);
 
 // kclique.cu
 void kclique_count(Graph &g, int k, uint64_t *out);

@@ -182,6 +182,21 @@ inline void degeneracy_ordering(const CudaSetGraph &g, Output &ranking) {
     check(gmsb_order_degeneracy(g.handle(), tmp.data()));
     for (int64_t i = 0; i < n; ++i) ranking[i] = tmp[i];
 }
+// approximate degeneracy order, averageDegree boundary (degeneracy_approx_csr.h:13-78); ascending convention
+template <bool useRankFormat = false, class Output = std::vector<NodeId>>
+inline void degeneracy_ordering_approx(const CudaSetGraph &g, Output &res, double epsilon) {
+    const int64_t n = g.num_nodes();
+    res.resize(n);
+    std::vector<NodeId> tmp(static_cast<size_t>(std::max<int64_t>(n, 1)));
+    check(gmsb_order_degeneracy_approx(g.handle(), epsilon, useRankFormat ? 1 : 0, tmp.data()));
+    for (int64_t i = 0; i < n; ++i) res[i] = tmp[i];
+}
+// the CLI's auto-relabel heuristic (gapbs/benchmark.h:158-176)
+inline bool WorthRelabelling(const CudaSetGraph &g) {
+    int w = 0;
+    check(gmsb_graph_worth_relabelling(g.handle(), &w));
+    return w != 0;
+}
 inline CudaSetGraph induce_directed_graph(const CudaSetGraph &g, const std::vector<NodeId> &ranking) {
     if (static_cast<int64_t>(ranking.size()) != g.num_nodes()) throw std::invalid_argument("ranking has wrong length");
     gmsb_graph_t h = nullptr;

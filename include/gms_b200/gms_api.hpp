@@ -137,6 +137,15 @@ void getDegreeOrdering(const AnyGraph &graph, Output &res) {
     static_assert(gms_b200::detail::is_cuda_graph<AnyGraph>, "gms-b200 implements this entry point for CudaSetGraph");
     gms_b200::degree_ordering<useRankFormat>(graph, res);
 }
+// getDegeneracyOrderingApproxCGraph<boundary, useRankFormat>(graph, res, epsilon)   parallel/degeneracy_approx_csr.h:13
+// (the averageDegree boundary is the one implemented; the sampled boundaries are randomised variants of it)
+namespace boundary_function { struct AverageDegree {}; constexpr AverageDegree averageDegree{}; }
+template <const boundary_function::AverageDegree &boundary = boundary_function::averageDegree, bool useRankFormat = false,
+          class CGraph = CudaSetGraph, class Output = std::vector<NodeId>>
+void getDegeneracyOrderingApproxCGraph(const CGraph &graph, Output &res, double epsilon) {
+    static_assert(gms_b200::detail::is_cuda_graph<CGraph>, "gms-b200 implements this entry point for CudaSetGraph");
+    gms_b200::degeneracy_ordering_approx<useRankFormat>(graph, res, epsilon);
+}
 }  // namespace PpParallel
 namespace PpSequential {
 template <class CGraph = CudaSetGraph, class Output>

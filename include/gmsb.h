@@ -92,6 +92,14 @@ GMSB_API int gmsb_order_degree(gmsb_graph_t g, int rank_format, int32_t *out);
  * a valid min-degree-peeling order in the reference's convention rank = n - (removal index); ties are
  * implementation-defined in the reference too. */
 GMSB_API int gmsb_order_degeneracy(gmsb_graph_t g, int32_t *out_rank);
+/* PpParallel::getDegeneracyOrderingApproxCGraph<boundary_function::averageDegree, useRankFormat>(g, out, epsilon)
+ *                                                       gms/algorithms/preprocessing/parallel/degeneracy_approx_csr.h:13-78
+ * rounds remove every vertex with residual degree <= (1+eps)*average; inside a round vertices are ordered by that
+ * degree (ties by id; unspecified in the reference). Ascending convention: first removed = position / rank 0. */
+GMSB_API int gmsb_order_degeneracy_approx(gmsb_graph_t g, double epsilon, int rank_format, int32_t *out);
+/* WorthRelabelling(g): the CLI's auto-relabel heuristic    gms/third_party/gapbs/benchmark.h:158-176, cli/cli.h:174-181
+ * (average degree >= 10 and mean/1.3 > median over 1000 mt19937-sampled non-isolated vertices). */
+GMSB_API int gmsb_graph_worth_relabelling(gmsb_graph_t g, int *out);
 /* PpSequential::InduceDirectedGraph(g, ranking)         gms/algorithms/preprocessing/sequential/apply_order.h:10-35
  * relabels u -> ranking[u], keeps rank(u) < rank(v); result n = max surviving id + 1. Fails with
  * GMSB_ERR_INVALID on a directed input (the reference throws std::invalid_argument, :14-16). */

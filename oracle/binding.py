@@ -175,11 +175,13 @@ class CpuLib:
                 "degeneracy_rank": (None, [C.c_void_p, _i32p]),
                 "check_degeneracy_rank": (C.c_int64, [C.c_void_p, _i32p]),
                 "core_number_of_rank": (C.c_int64, [C.c_void_p, _i32p]),
+                "adg_order": (None, [C.c_void_p, C.c_double, C.c_int, _i32p, _i32p]),
                 "tc_bytes": (None, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                     C.POINTER(C.c_int64)]),
             })
         else:
             sig.update({"degeneracy_danisch_heap": (None, [C.c_void_p, _i32p]),
+                        "adg_order": (None, [C.c_void_p, C.c_double, C.c_int, _i32p]),
                         "load_file": (C.c_void_p, [C.c_char_p, C.c_int]),
                         "write_file": (None, [C.c_void_p, C.c_char_p, C.c_int])})
         self._fn = {}
@@ -274,6 +276,16 @@ class CpuLib:
 
     def check_degeneracy_rank(self, g, rank):
         return int(self._f("check_degeneracy_rank")(g.h, np.ascontiguousarray(rank, np.int32)))
+
+    def adg_order(self, g, eps=1.0, rank_format=False):
+        """Approximate degeneracy order (averageDegree boundary). The oracle also returns the round of each vertex."""
+        out = np.zeros(max(g.n, 1), np.int32)
+        if self.prefix == "orc_":
+            rounds = np.zeros(max(g.n, 1), np.int32)
+            self._f("adg_order")(g.h, float(eps), int(rank_format), out, rounds)
+            return out[:g.n], rounds[:g.n]
+        self._f("adg_order")(g.h, float(eps), int(rank_format), out)
+        return out[:g.n]
 
     def core_number_of_rank(self, g, rank):
         return int(self._f("core_number_of_rank")(g.h, np.ascontiguousarray(rank, np.int32)))

@@ -485,6 +485,39 @@ double orc_tc_total_sample(void *h, int64_t stride, int64_t phase, int64_t *edge
 void orc_degree_order(void *h, int rank_format, int32_t *out) { degree_order(*G(h), rank_format != 0, out); }
 void orc_degeneracy_rank(void *h, int32_t *rank_out) { degeneracy_rank(*G(h), rank_out); }
 int64_t orc_check_degeneracy_rank(void *h, const int32_t *rank) { return check_degeneracy_rank(*G(h), rank); }
+// Approximate degeneracy order, averageDegree boundary (preprocessing/parallel/degeneracy_approx_csr.h:13-78,
+// boundary_function.h:15-25): each round removes every remaining vertex with degree counter <= (unsigned)((1+eps) *
+// mean counter of the remaining), ordered inside the round by that counter (the reference's parallel partition + sort
+// leave ties unspecified; here ties go by id), then decrements the counter of EVERY neighbour (push style).
+// round_of (optional) receives the round in which each vertex left, for batch-level comparison with the reference.
+void orc_adg_order(void *h, double eps, int rank_format, int32_t *out, int32_t *round_of) {
+    const Graph &g = *G(h);
+    const int64_t n = g.n;
+    std::vector<int> cnt(n);
+    std::vector<vid> live(n);
+    for (int64_t v = 0; v < n; ++v) { cnt[v] = (int)g.deg((vid)v); live[v] = (vid)v; }
+    int64_t done = 0;
+    int32_t round = 0;
+    while (done < n) {
+        double res = 0;
+        for (vid v : live) res += cnt[v];
+        unsigned int border = (unsigned int)((1 + eps) * (res / (double)live.size()));
+        std::vector<vid> batch, rest;
+        for (vid v : live) ((long long)cnt[v] <= (long long)border ? batch : rest).push_back(v);
+        std::sort(batch.begin(), batch.end(), [&](vid a, vid b) { return cnt[a] < cnt[b] || (cnt[a] == cnt[b] && a < b); });
+        for (size_t i = 0; i < batch.size(); ++i) {
+            vid v = batch[i];
+            if (rank_format) out[v] = (int32_t)(done + i); else out[done + i] = v;
+            if (round_of) round_of[v] = round;
+        }
+        for (vid v : batch)
+            for (const vid *p = g.begin(v); p != g.end(v); ++p) cnt[*p]--;
+        done += (int64_t)batch.size();
+        live.swap(rest);
+        ++round;
+    }
+}
+
 // The reference's own acceptance test for a degeneracy order (verifiers/degeneracy_verifier.h:69-85), in rank
 // format: with removal order = descending rank, every vertex may have at most `degeneracy` neighbours removed
 // after it.  Returns max_v |{w in N(v): rank[w] < rank[v]}| (the "core number of the order"), or -1 if rank is

@@ -287,6 +287,15 @@ void gmsref_degeneracy_danisch_heap(void *h, int32_t *rank_out) {
     PpSequential::getDegeneracyOrderingDanischHeap(g, ranking);
     std::memcpy(rank_out, ranking.data(), sizeof(NodeId) * ranking.size());
 }
+void gmsref_adg_order(void *h, double eps, int rank_format, int32_t *out) {
+    const CSRGraph &g = static_cast<RefGraph *>(h)->g;
+    std::vector<NodeId> res;
+    if (rank_format)
+        PpParallel::getDegeneracyOrderingApproxCGraph<PpParallel::boundary_function::averageDegree, true>(g, res, eps);
+    else
+        PpParallel::getDegeneracyOrderingApproxCGraph<PpParallel::boundary_function::averageDegree, false>(g, res, eps);
+    std::memcpy(out, res.data(), sizeof(NodeId) * res.size());
+}
 void *gmsref_induce_directed(void *h, const int32_t *ranking) {
     Quiet q;
     const CSRGraph &g = static_cast<RefGraph *>(h)->g;
