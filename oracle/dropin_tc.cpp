@@ -1,8 +1,10 @@
-// TEST INFRASTRUCTURE ONLY — the drop-in demonstration: the reference's OWN benchmark main
-// (examples/triangle_counting.cpp, gms/algorithms/set_based/triangle_count/triangle_count.cc) with the graph type
-// swapped for gms_b200::CudaSetGraph.  Everything else — CLI parsing, generator, builder, auto-relabel,
-// BenchmarkKernelBk, the -v verifier (Verify::total_count, Verify::vertex_count<2>) and the @@@ result lines —
-// is the unmodified reference, compiled from where it lies by oracle/Makefile into oracle/_ref/dropin_tc.
+// TEST INFRASTRUCTURE ONLY — the drop-in demonstration.
+//
+// A benchmark main in the shape of the reference's own triangle-count mains, but with gms_b200::CudaSetGraph as the
+// graph type.  Everything it calls besides CudaSetGraph is the UNMODIFIED reference, compiled from where it lies by
+// oracle/Makefile into oracle/_ref/dropin_tc: the CLI (parse_and_load: generator, builder, auto-relabel), the
+// harness (BenchmarkKernelBk: FromCGraph once, kernel per trial, "@@@" result lines) and the -v verifiers
+// (Verify::total_count, Verify::vertex_count<2>), which therefore check the GPU results at run time.
 //
 //   oracle/_ref/dropin_tc -g kronecker 16 --deg 16 -n 3 -v
 #include <gms/third_party/gapbs/benchmark.h>
@@ -16,30 +18,31 @@
 #define GMSB_WITH_GMS_HEADERS
 #include <gms_b200/gms_api.hpp>
 
-using namespace GMS;
-using namespace GMS::TriangleCount;
+namespace tc = GMS::TriangleCount;
+using GMS::BenchmarkKernelBk;
 using gms_b200::CudaSetGraph;
 
-template <class AnyGraph, class Fn>
-constexpr auto output_wrap(Fn fn) {
-    return [fn{std::move(fn)}](const AnyGraph &g) {
-        std::vector<int64_t> output;
-        fn(g, output);
-        return output;
-    };
-}
-
 int main(int argc, char *argv[]) {
-    auto [args, g] = CLI::Parser().parse_and_load(argc, argv);
+    auto loaded = GMS::CLI::Parser().parse_and_load(argc, argv);
+    GMS::CLI::Args &args = std::get<0>(loaded);
+    CSRGraph &host_graph = std::get<1>(loaded);
 
-    // the B200 path behind the reference's harness
-    BenchmarkKernelBk<CudaSetGraph>(args, g, Par::count_total<CudaSetGraph>, Verify::total_count,
+    // total count: the B200 path behind the reference's harness and verifier
+    BenchmarkKernelBk<CudaSetGraph>(args, host_graph, tc::Par::count_total<CudaSetGraph>, tc::Verify::total_count,
                                     "tc-total-par-CudaSetGraph");
-    BenchmarkKernelBk<CudaSetGraph>(args, g, output_wrap<CudaSetGraph>(Par::vertex_count2<CudaSetGraph, std::vector<int64_t>>),
-                                    Verify::vertex_count<2>, "tc-vertex-count2-par-CudaSetGraph");
-    // the reference's own SortedSet path, for the side-by-side @@@ line
-    if (g.num_nodes() <= (1 << 18))
-        BenchmarkKernelBk<SortedSetGraph>(args, g, Par::count_total<SortedSetGraph>, Verify::total_count,
-                                          "tc-total-par-SortedSetGraph");
+
+    // per-vertex counts: the harness wants a kernel that RETURNS its result
+    auto per_vertex = [](const CudaSetGraph &g) {
+        std::vector<int64_t> counts;
+        tc::Par::vertex_count2<CudaSetGraph, std::vector<int64_t>>(g, counts);
+        return counts;
+    };
+    BenchmarkKernelBk<CudaSetGraph>(args, host_graph, per_vertex, tc::Verify::vertex_count<2>,
+                                    "tc-vertex-count2-par-CudaSetGraph");
+
+    // the reference's own SortedSet path on the same graph, for the side-by-side "@@@" line (small graphs only)
+    if (host_graph.num_nodes() <= (1 << 18))
+        BenchmarkKernelBk<SortedSetGraph>(args, host_graph, tc::Par::count_total<SortedSetGraph>,
+                                          tc::Verify::total_count, "tc-total-par-SortedSetGraph");
     return 0;
 }
