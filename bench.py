@@ -283,6 +283,12 @@ def run_ours(args):
         "algorithmic_bytes_per_launch": frac_share, "kernel_ms": bm_ms,
         "all_count_kernels": {"algorithmic_bytes": st["algorithmic_bytes"], "ms": count_ms,
                               "achieved": st["algorithmic_bytes"] / (count_ms * 1e-3) / 1e9 if count_ms else 0.0},
+        # what the kernel actually asks the memory system for: 4 B per probed list element + 8 B per descriptor
+        "requested_load": (lambda b: {"bytes_per_launch": b, "GBps": b / (bm_ms * 1e-3) / 1e9 if bm_ms else 0.0,
+                                      "frac_of_peak": b / (bm_ms * 1e-3) / 1e9 / peak if bm_ms else 0.0})(
+            4 * st["wedges_bitmap"] / max(world, 1) + 8 * st["edges_bitmap"]),
+        "dram_frac_of_peak": (ncu_traffic("k_tc_bitmap") / (bm_ms * 1e-3) / 1e9 / peak
+                              if world == 1 and bm_ms and ncu_traffic("k_tc_bitmap") else None),
         "note": "algorithmic bytes = sum over oriented edges of 4*(d+(u)+d+(v)) (SURVEY.md 8d); the kernel reads "
                 "only the suffix of N+(u) after v and probes an on-chip bitmap of N+(v), so DRAM traffic is far "
                 "below the algorithmic bytes and frac can exceed 1",
