@@ -89,6 +89,31 @@ __global__ void k_relabel_keys(const eid_t *__restrict__ off, const vid_t *__res
     }
 }
 
+// flags[0]: malformed (offsets decrease, id outside [0,n)); flags[1]: some list is not ascending
+__global__ void k_check_csr(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, int64_t n, int *flags) {
+    int lane = threadIdx.x & 31;
+    int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t u = warp; u < n; u += nwarps) {
+        eid_t b = off[u], e = off[u + 1];
+        if (e < b) { if (lane == 0) flags[0] = 1; continue; }
+        for (eid_t s = b + lane; s < e; s += 32) {
+            vid_t v = nbr[s];
+            if (v < 0 || v >= n) flags[0] = 1;
+            if (s > b && nbr[s - 1] > v) flags[1] = 1;
+        }
+    }
+}
+// (u << 32 | v) for every slot: a radix sort of these keys sorts each list and keeps the lists in place
+__global__ void k_slot_keys(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, int64_t n,
+                            uint64_t *__restrict__ keys) {
+    int lane = threadIdx.x & 31;
+    int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t u = warp; u < n; u += nwarps)
+        for (eid_t s = off[u] + lane; s < off[u + 1]; s += 32) keys[s] = ((uint64_t)u << 32) | (uint32_t)nbr[s];
+}
+
 __global__ void k_low32(const uint64_t *__restrict__ keys, int64_t K, vid_t *__restrict__ out) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < K; i += (int64_t)gridDim.x * blockDim.x)
         out[i] = (vid_t)(uint32_t)keys[i];
@@ -119,6 +144,22 @@ Graph *graph_from_csr_device(int64_t n, const eid_t *off, const vid_t *nbr, bool
         g->slots = last;
         g->nbr.alloc(last);
         if (last) GMSB_CUDA(cudaMemcpyAsync(g->nbr.p, nbr, sizeof(vid_t) * last, kind, r.stream));
+        // SortedSet's constructor sorts what it is given (sorted_set.h:64-66, so FromCGraph accepts any list order);
+        // here one streaming pass checks monotone offsets, id range and order, and only an unsorted CSR pays for a sort.
+        if (last && n) {
+            DevBuf<int> flags(2);
+            flags.zero();
+            k_check_csr<<<grid_for(n * 32, 256), 256, 0, r.stream>>>(g->off.p, g->nbr.p, n, flags.p); launched();
+            int h[2];
+            flags.download(h, 2);
+            GMSB_REQUIRE(h[0] == 0, "graph_from_csr: offsets not monotone or neighbour id out of range");
+            if (h[1]) {
+                DevBuf<uint64_t> keys(last), alt(last);
+                k_slot_keys<<<grid_for(n * 32, 256), 256, 0, r.stream>>>(g->off.p, g->nbr.p, n, keys.p); launched();
+                uint64_t *sorted = radix_sort_keys(keys.p, alt.p, last, 0, 32 + bits_for((uint64_t)(n - 1)));
+                k_low32<<<grid_for(last, 256), 256, 0, r.stream>>>(sorted, last, g->nbr.p); launched();
+            }
+        }
         GMSB_CUDA(cudaStreamSynchronize(r.stream));
     } catch (...) { delete g; throw; }
     return g;

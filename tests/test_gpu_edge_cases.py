@@ -115,6 +115,29 @@ def test_dense_graph_with_long_oriented_lists(gms, orc):
     # (the oracle needs minutes for 4-cliques at this density; k >= 4 is covered on sparser graphs)
 
 
+def test_from_csr_accepts_unsorted_lists_and_rejects_malformed(gms, orc):
+    """SortedSet's constructor sorts its input (sorted_set.h:64-66), so FromCGraph works on any list order."""
+    s, d = random_graph_edges(12, 800, 9000, skew=0.8)
+    o = orc.from_el(s, d, True)
+    off, nbr = o.csr()
+    rng = np.random.default_rng(0)
+    shuffled = nbr.copy()
+    for u in range(len(off) - 1):
+        rng.shuffle(shuffled[off[u]:off[u + 1]])
+    g = gms.Graph.from_csr(off, shuffled)
+    eo, en = g.export_csr()
+    assert (eo == off).all() and (en == nbr).all() and g.tc_total() == o.tc_total()
+    bad = nbr.copy()
+    bad[3] = len(off) + 5
+    with pytest.raises(gms.GmsbError):
+        gms.Graph.from_csr(off, bad)
+    bad_off = off.copy()
+    bad_off[5], bad_off[6] = bad_off[6], bad_off[5] - 1 if bad_off[5] > 0 else 0
+    if (np.diff(bad_off) < 0).any():
+        with pytest.raises(gms.GmsbError):
+            gms.Graph.from_csr(bad_off, nbr)
+
+
 def test_degenerate_clique_sizes_and_errors(gms):
     s, d = clique_edges(6)
     g = gms.Graph.from_edgelist(s, d, True)
