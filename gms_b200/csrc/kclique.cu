@@ -178,9 +178,25 @@ __device__ unsigned long long compact_count(const uint32_t *rows, int W, const W
         ws->cm[a] = mask;
     }
     __syncwarp();
-    // 3. member a is the next clique vertex; need-1 more inside its compact row
+    // 3. member a is the next clique vertex; need-1 more inside its compact row.  With two or more levels left the
+    //    work is dealt out as (a, b) PAIRS — lane t takes the t-th out-neighbour b of a — so that 32 lanes share one
+    //    member's subtree instead of each lane owning a whole (and very unequal) subtree.
     unsigned long long total = 0;
-    for (int a = lane; a < c; a += 32) total += dfs64(ws->cm, ws->cm[a], need - 1);
+    if (need - 1 == 1) {
+        for (int a = lane; a < c; a += 32) total += __popcll(ws->cm[a]);
+        return total;
+    }
+    for (int a = 0; a < c; ++a) {
+        const unsigned long long ra = ws->cm[a];
+        const int na = __popcll(ra);
+        if (na < need - 1) continue;
+        const unsigned lo = (unsigned)ra, hi = (unsigned)(ra >> 32);
+        const int nlo = __popc(lo);
+        for (int t = lane; t < na; t += 32) {
+            const int b = t < nlo ? (int)__fns(lo, 0, t + 1) : 32 + (int)__fns(hi, 0, t - nlo + 1);
+            total += dfs64(ws->cm, ra & ws->cm[b], need - 2);
+        }
+    }
     return total;
 }
 
