@@ -176,6 +176,7 @@ class CpuLib:
                 "check_degeneracy_rank": (C.c_int64, [C.c_void_p, _i32p]),
                 "core_number_of_rank": (C.c_int64, [C.c_void_p, _i32p]),
                 "adg_order": (None, [C.c_void_p, C.c_double, C.c_int, _i32p, _i32p]),
+                "clique_counts_pivot": (None, [C.c_void_p, C.c_int, np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")]),
                 "tc_bytes": (None, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                     C.POINTER(C.c_int64)]),
             })
@@ -286,6 +287,12 @@ class CpuLib:
             return out[:g.n], rounds[:g.n]
         self._f("adg_order")(g.h, float(eps), int(rank_format), out)
         return out[:g.n]
+
+    def clique_counts_pivot(self, dag, kmax):
+        """counts[k] for k = 0..kmax on an oriented DAG, by pivoting (independent cross-check, oracle only)."""
+        out = np.zeros(kmax + 1, np.uint64)
+        self._f("clique_counts_pivot")(dag.h, kmax, out)
+        return [int(x) for x in out]
 
     def core_number_of_rank(self, g, rank):
         return int(self._f("core_number_of_rank")(g.h, np.ascontiguousarray(rank, np.int32)))

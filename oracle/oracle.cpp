@@ -339,6 +339,81 @@ uint64_t dag_cliques(const Graph &g, int k) {
     }
     return total;
 }
+// Independent cross-check for larger k (NOT a reference restatement): clique counts for every size 1..kmax at once by
+// pivoting on the undirected subgraph induced by N+(u) (succinct clique tree, Jain & Seshadhri, WSDM 2020).  It
+// reproduces every reference-measured count of SURVEY.md §8c (e.g. kronecker-14: k=8 -> 138 220 170 775) with a
+// different algorithm than both the reference and the CUDA kernels, so it pins k = 7..10 where the reference's
+// one-by-one enumeration would take hours.  `dag` must be an oriented DAG (ids ascending along edges).
+struct PivotSub {
+    int D, W;
+    std::vector<uint64_t> adj;          // D rows of W words, symmetric
+};
+unsigned __int128 binom128(int n, int r) {
+    if (r < 0 || r > n) return 0;
+    unsigned __int128 x = 1;
+    for (int i = 0; i < r; ++i) x = x * (unsigned)(n - i) / (unsigned)(i + 1);
+    return x;
+}
+void pivot_rec(const PivotSub &s, std::vector<uint64_t> &cand, int held, int pivots, int kmax, unsigned __int128 *cnt) {
+    const int W = s.W;
+    bool empty = true;
+    for (int i = 0; i < W; ++i) if (cand[i]) { empty = false; break; }
+    if (empty || held > kmax) {
+        for (int k = held; k <= kmax && k <= held + pivots; ++k) cnt[k] += binom128(pivots, k - held);
+        return;
+    }
+    int best = -1, best_c = -1;
+    for (int w = 0; w < W; ++w)
+        for (uint64_t m = cand[w]; m; m &= m - 1) {
+            const int x = w * 64 + __builtin_ctzll(m);
+            int c = 0;
+            for (int i = 0; i < W; ++i) c += __builtin_popcountll(cand[i] & s.adj[(size_t)x * W + i]);
+            if (c > best_c) { best_c = c; best = x; }
+        }
+    std::vector<uint64_t> nxt(W), todo(W);
+    for (int i = 0; i < W; ++i) {
+        nxt[i] = cand[i] & s.adj[(size_t)best * W + i];
+        todo[i] = cand[i] & ~s.adj[(size_t)best * W + i];
+    }
+    todo[best / 64] &= ~(1ull << (best % 64));
+    cand[best / 64] &= ~(1ull << (best % 64));
+    pivot_rec(s, nxt, held, pivots + 1, kmax, cnt);              // pivot link: cliques may or may not use `best`
+    for (int w = 0; w < W; ++w)
+        for (uint64_t m = todo[w]; m; m &= m - 1) {
+            const int b = __builtin_ctzll(m), x = w * 64 + b;
+            for (int i = 0; i < W; ++i) nxt[i] = cand[i] & s.adj[(size_t)x * W + i];
+            cand[w] &= ~(1ull << b);
+            pivot_rec(s, nxt, held + 1, pivots, kmax, cnt);      // hold link: cliques that contain x
+        }
+}
+void clique_counts_pivot(const Graph &dag, int kmax, uint64_t *out /* kmax+1 */) {
+    std::vector<unsigned __int128> total(kmax + 1, 0);
+    #pragma omp parallel
+    {
+        std::vector<unsigned __int128> local(kmax + 1, 0);
+        #pragma omp for schedule(dynamic, 1)
+        for (int64_t u = dag.n - 1; u >= 0; --u) {
+            const vid *S = dag.begin((vid)u);
+            const int D = (int)dag.deg((vid)u);
+            PivotSub s;
+            s.D = D; s.W = (D + 63) / 64;
+            s.adj.assign((size_t)D * std::max(s.W, 1), 0);
+            for (int i = 0; i < D; ++i)
+                for (int j = i + 1; j < D; ++j)
+                    if (std::binary_search(dag.begin(S[i]), dag.end(S[i]), S[j])) {
+                        s.adj[(size_t)i * s.W + j / 64] |= 1ull << (j % 64);
+                        s.adj[(size_t)j * s.W + i / 64] |= 1ull << (i % 64);
+                    }
+            std::vector<uint64_t> cand(std::max(s.W, 1), 0);
+            for (int i = 0; i < D; ++i) cand[i / 64] |= 1ull << (i % 64);
+            pivot_rec(s, cand, 1, 0, kmax, local.data());        // u itself is held
+        }
+        #pragma omp critical
+        for (int k = 0; k <= kmax; ++k) total[k] += local[k];
+    }
+    for (int k = 0; k <= kmax; ++k) out[k] = (uint64_t)total[k];
+}
+
 // Set-based CliqueCount on the unoriented graph (k_clique_count/k_clique_count_set_based.h:6-31): counts
 // ordered tuples, i.e. returns k!·C_k; the prune test |cur| >= k-2 uses the CURRENT k, kept verbatim.
 uint64_t ordered_cliques_rec(const Graph &g, uint64_t k, const std::vector<vid> &s) {
@@ -546,6 +621,7 @@ double orc_kclique_timed(void *h, int k, int mode, uint64_t *out) {
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 uint64_t orc_clique_count_set_based(void *h, int k) { return ordered_cliques(*G(h), k); }
+void orc_clique_counts_pivot(void *h, int kmax, uint64_t *out) { clique_counts_pivot(*G(h), kmax, out); }
 
 double orc_vertex_similarity(void *h, int metric, int32_t a, int32_t b) { return similarity(*G(h), metric, a, b); }
 void orc_pair_similarity(void *h, int metric, int64_t np, const int32_t *a, const int32_t *b, double *out) {
