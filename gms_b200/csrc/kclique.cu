@@ -28,7 +28,12 @@ namespace gmsb {
 namespace {
 
 constexpr int kMaxK = 16;
-constexpr int kBigBlock = 512;
+
+// bit-matrix geometry: rows of an even number of 32-bit words (so they can be walked as 64-bit words)
+__host__ __device__ inline int row_words(int D) { return ((D + 63) >> 6) << 1; }
+__host__ __device__ inline size_t matrix_words(int D) {
+    return (size_t)((D + 1) & ~1) + (size_t)D * (size_t)row_words(D);
+}
 
 // ---- d+(u) <= 32 -----------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long dfs32(const uint32_t *rows, uint32_t cand, int need) {
@@ -143,10 +148,10 @@ __device__ unsigned long long dfs64(const unsigned long long *cm, unsigned long 
 // `need`-cliques inside the warp-distributed set `cand` of c <= 64 members (need >= 2); per-lane partial count.
 // The recursion below this point never touches the big matrix again: each lane runs the search of one (or two)
 // first members with register masks, which is ~30x cheaper per clique than a warp-wide step.
+// ascending list of the positions of a warp-distributed set's members (<= 64 of them) in ws->list.
+// word w = lane + 32*slot, so the order is slot-major, then lane, then bit.
 template <int WPL>
-__device__ unsigned long long compact_count(const uint32_t *rows, int W, const WarpSet<WPL> &cand, int c, int need,
-                                            int lane, WarpScratch *ws) {
-    // 1. ascending list of member positions: word w = lane + 32*slot, so order is slot-major then lane
+__device__ __forceinline__ void list_members(const WarpSet<WPL> &cand, int lane, WarpScratch *ws) {
     int base = 0;
     __syncwarp();
 #pragma unroll
@@ -167,6 +172,41 @@ __device__ unsigned long long compact_count(const uint32_t *rows, int W, const W
         base += __shfl_sync(0xffffffffu, incl, 31);
     }
     __syncwarp();
+}
+
+// Last two levels for a SMALL candidate set (c <= 64 members): the members are listed once, lane t takes members
+// t and t+32, and each walks only the 64-bit words between its own position and the set's last member — candidate
+// sets deep in the search cluster at the hub end of S, so that is usually two or three words.
+template <int WPL>
+__device__ unsigned long long pair_count_small(const uint32_t *rows, int W, const WarpSet<WPL> &cset, int c, int lane,
+                                               WarpScratch *ws) {
+    list_members<WPL>(cset, lane, ws);
+    uint32_t *cw = reinterpret_cast<uint32_t *>(ws->cm);
+#pragma unroll
+    for (int s = 0; s < WPL; ++s) {
+        const int w = lane + (s << 5);
+        if (w < W) cw[w] = cset.w[s];
+    }
+    __syncwarp();
+    const unsigned long long *cw64 = reinterpret_cast<const unsigned long long *>(cw);
+    const int last = ws->list[c - 1] >> 6;
+    unsigned long long total = 0;
+    for (int a = lane; a < c; a += 32) {
+        const int l = ws->list[a];
+        const unsigned long long *row64 = reinterpret_cast<const unsigned long long *>(rows + (size_t)l * W);
+        uint32_t cnt = 0;
+        for (int x = l >> 6; x <= last; ++x) cnt += __popcll(cw64[x] & row64[x]);
+        total += cnt;
+    }
+    __syncwarp();
+    return total;
+}
+
+template <int WPL>
+__device__ unsigned long long compact_count(const uint32_t *rows, int W, const WarpSet<WPL> &cand, int c, int need,
+                                            int lane, WarpScratch *ws) {
+    // 1. ascending list of member positions
+    list_members<WPL>(cand, lane, ws);
     // 2. compact adjacency: only later members can be out-neighbours (positions ascend with vertex id)
     for (int a = lane; a < c; a += 32) {
         const uint32_t *row = rows + (size_t)ws->list[a] * W;
@@ -222,9 +262,11 @@ __device__ unsigned long long pair_count(const uint32_t *rows, int W, const Warp
         while (word) {
             const int l = (w << 5) + __ffs(word) - 1;
             word &= word - 1;
-            const uint32_t *row = rows + (size_t)l * W;
+            // row_l only has members after l; rows are 8-byte aligned with an even word count -> 64-bit steps
+            const unsigned long long *row64 = reinterpret_cast<const unsigned long long *>(rows + (size_t)l * W);
+            const unsigned long long *cw64 = reinterpret_cast<const unsigned long long *>(cw);
             uint32_t cnt = 0;
-            for (int x = w; x < W; ++x) cnt += __popc(cw[x] & row[x]);    // row_l only has members after l
+            for (int x = w >> 1; x < (W >> 1); ++x) cnt += __popcll(cw64[x] & row64[x]);
             total += cnt;
         }
     }
@@ -245,7 +287,9 @@ __device__ unsigned long long dfs_warp(const uint32_t *rows, int W, WarpSet<WPL>
         int all = pc0;
         for (int o = 16; o; o >>= 1) all += __shfl_xor_sync(0xffffffffu, all, o);
         if (all < need) return 0;
-        if (all <= 64) return compact_count<WPL>(rows, W, cand, all, need, lane, ws);
+        if (all <= 64)
+            return need == 2 ? pair_count_small<WPL>(rows, W, cand, all, lane, ws)
+                             : compact_count<WPL>(rows, W, cand, all, need, lane, ws);
         if (need == 2) return pair_count<WPL>(rows, W, cand, lane, ws);
     }
     WarpSet<WPL> it[kMaxK - 2], cur[kMaxK - 2];
@@ -277,7 +321,9 @@ __device__ unsigned long long dfs_warp(const uint32_t *rows, int W, WarpSet<WPL>
             int all = pc;
             for (int o = 16; o; o >>= 1) all += __shfl_xor_sync(0xffffffffu, all, o);
             if (all >= left) {
-                if (all <= 64) total += compact_count<WPL>(rows, W, nxt, all, left, lane, ws);
+                if (all <= 64)
+                    total += left == 2 ? pair_count_small<WPL>(rows, W, nxt, all, lane, ws)
+                                       : compact_count<WPL>(rows, W, nxt, all, left, lane, ws);
                 else if (left == 2) total += pair_count<WPL>(rows, W, nxt, lane, ws);
                 else { ++level; cur[level] = nxt; it[level] = nxt; }
             }
@@ -286,8 +332,8 @@ __device__ unsigned long long dfs_warp(const uint32_t *rows, int W, WarpSet<WPL>
     return total;
 }
 
-template <int WPL>
-__global__ void __launch_bounds__(kBigBlock)
+template <int WPL, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB)
 k_kclique_big(const vid_t *__restrict__ verts, const int64_t *__restrict__ item_base, int64_t nverts, int64_t count,
               const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, int k, int maxD,
               unsigned long long *__restrict__ total, unsigned int *__restrict__ ticket,
@@ -295,15 +341,15 @@ k_kclique_big(const vid_t *__restrict__ verts, const int64_t *__restrict__ item_
     extern __shared__ uint32_t smem[];
     // member list + bit matrix live in shared memory, or — when max d+ makes them larger than an SM's shared
     // memory — in this CTA's slice of a global scratch buffer (L2-resident for the sizes that occur)
-    uint32_t *store = spill ? spill + (size_t)blockIdx.x * ((size_t)maxD + (size_t)maxD * ((maxD + 31) >> 5)) : smem;
-    vid_t *S = reinterpret_cast<vid_t *>(store);           // maxD members
-    uint32_t *rows = store + maxD;                         // D x W bit matrix
-    __shared__ unsigned long long red[kBigBlock / 32];
-    __shared__ WarpScratch scratch[kBigBlock / 32];
+    uint32_t *store = spill ? spill + (size_t)blockIdx.x * matrix_words(maxD) : smem;
+    vid_t *S = reinterpret_cast<vid_t *>(store);           // maxD members (padded to an even count)
+    uint32_t *rows = store + ((maxD + 1) & ~1);            // D x W bit matrix, W even so rows are 8-byte aligned
+    __shared__ unsigned long long red[BLOCK / 32];
+    __shared__ WarpScratch scratch[BLOCK / 32];
     __shared__ unsigned int s_item;
     __shared__ int s_next;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = kBigBlock / 32;
+    constexpr int NW = BLOCK / 32;
     unsigned long long acc = 0;
     for (;;) {
         __syncthreads();
@@ -323,9 +369,9 @@ k_kclique_big(const vid_t *__restrict__ verts, const int64_t *__restrict__ item_
         const vid_t u = verts[t];
         const eid_t ob = off[u];
         const int D = (int)(off[u + 1] - ob);
-        const int W = (D + 31) >> 5;
-        for (int j = tid; j < D; j += kBigBlock) S[j] = nbr[ob + j];
-        for (int j = tid; j < D * W; j += kBigBlock) rows[j] = 0u;
+        const int W = row_words(D);
+        for (int j = tid; j < D; j += BLOCK) S[j] = nbr[ob + j];
+        for (int j = tid; j < D * W; j += BLOCK) rows[j] = 0u;
         __syncthreads();
         // rows: warp per member i streams N+(S[i]) and looks every element up in S
         for (int i = warp; i < D; i += NW) {
@@ -399,7 +445,9 @@ __global__ void k_parts(const vid_t *__restrict__ verts, int64_t cnt, const eid_
         const vid_t u = verts[i];
         const int64_t d = off[u + 1] - off[u];
         // for k <= 4 building the matrix dominates, so a vertex stays whole; deeper searches are cut finer
-        parts[i] = k <= 4 ? 1 : (d > kMidD ? (d + 63) / 64 : (d + 127) / 128);
+        // (every part rebuilds the vertex's matrix, so parts are kept few: the split is only there to spread the
+        // handful of densest neighbourhoods over several SMs)
+        parts[i] = k <= 4 ? 1 : (d > kMidD ? (d + 255) / 256 : 1);
         if (d > kMidD) atomicAdd(nhuge, 1);
     }
 }
@@ -438,7 +486,7 @@ uint64_t count_on_dag(int64_t n, int64_t m, const eid_t *off, const vid_t *nbr, 
         k_degree_key<<<grid_for(nb, 256), 256, 0, r.stream>>>(vb.p, nb, off, keys.p); launched();
         uint64_t *sorted = radix_sort_keys(keys.p, alt.p, nb, 0, 64, /*descending=*/true);
         k_key_vertex<<<grid_for(nb, 256), 256, 0, r.stream>>>(sorted, nb, vb.p); launched();
-        if (((maxD + 31) >> 5) > 128)
+        if (row_words(maxD) > 128)
             throw Error(GMSB_ERR_UNSUPPORTED, "kclique_count: max out-degree " + std::to_string(maxD) +
                                                   " exceeds 4096; orient by degree or degeneracy first");
         // work items: (vertex, interleaved part of its second-level members)
@@ -448,37 +496,43 @@ uint64_t count_on_dag(int64_t n, int64_t m, const eid_t *off, const vid_t *nbr, 
         k_parts<<<grid_for(nb, 256), 256, 0, r.stream>>>(vb.p, nb, off, k, parts.p, nhuge.p); launched();
         const int64_t n_huge = nhuge.get(0);           // vertices with d+ > kMidD come first (sorted descending)
         // two launches so that the many mid-size neighbourhoods get a small matrix and several CTAs per SM
-        auto run_class = [&](int64_t first, int64_t cnt, int classD) {
+        auto run_class = [&](int64_t first, int64_t cnt, int classD, bool huge) {
             if (cnt == 0) return;
             exclusive_sum(parts.p + first, item_base.p, cnt + 1);
             const int64_t n_items = item_base.get(cnt);
-            const int W = (classD + 31) >> 5;
-            const size_t need = ((size_t)classD + (size_t)classD * W) * 4;
-            const bool in_smem = need + 16 * 1024 <= r.smem_optin;    // static scratch (WarpScratch etc.) is ~13 KB
+            const int W = row_words(classD);
+            const size_t need = matrix_words(classD) * 4;
+            const bool in_smem = need + 28 * 1024 <= r.smem_optin;    // static scratch (WarpScratch etc.) is <= 25 KB
             const size_t smem = in_smem ? need : 0;
             DevBuf<unsigned int> ticket(1);
             ticket.zero();
             DevBuf<uint32_t> spill;
-            auto launch = [&](auto kern) {
+            auto launch = [&](auto kern, int block) {
                 if (smem > 48 * 1024)
                     GMSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 int resident = 0;
-                GMSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, kBigBlock, smem));
+                GMSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, block, smem));
                 GMSB_REQUIRE(resident >= 1, "kclique_count: kernel does not fit on an SM");
                 if (!in_smem) resident = 1;
                 const int grid = (int)std::min<int64_t>(n_items, (int64_t)r.sm_count * resident);
                 if (!in_smem) spill.alloc((size_t)grid * (need / 4));
-                kern<<<grid, kBigBlock, smem, r.stream>>>(vb.p + first, item_base.p, cnt, n_items, off, nbr, k, classD,
+                kern<<<grid, block, smem, r.stream>>>(vb.p + first, item_base.p, cnt, n_items, off, nbr, k, classD,
                                                           total.p, ticket.p, in_smem ? nullptr : spill.p);
                 launched();
                 GMSB_CUDA(cudaStreamSynchronize(r.stream));
             };
-            if (W <= 32) launch(k_kclique_big<1>);
-            else if (W <= 64) launch(k_kclique_big<2>);
-            else launch(k_kclique_big<4>);
+            // the search is a chain of dependent shared-memory steps, so resident warps are what hides its latency:
+            // a big matrix fills the SM's shared memory -> one CTA of 1024 threads; mid-size ones -> 2 x 512
+            if (huge) {
+                if (W <= 32) launch(k_kclique_big<1, 1024, 1>, 1024);
+                else if (W <= 64) launch(k_kclique_big<2, 1024, 1>, 1024);
+                else launch(k_kclique_big<4, 1024, 1>, 1024);
+            } else {
+                launch(k_kclique_big<1, 512, 2>, 512);        // kMidD = 512 -> W = 16
+            }
         };
-        run_class(0, n_huge, maxD);
-        run_class(n_huge, nb - n_huge, kMidD);
+        run_class(0, n_huge, maxD, true);
+        run_class(n_huge, nb - n_huge, kMidD, false);
     }
     return total.get(0);
 }
@@ -509,8 +563,8 @@ void kclique_count(Graph &g, int k, uint64_t *out) {
         DevBuf<int> mx(1);
         mx.zero();
         k_max_out<<<grid_for(g.n, 256), 256, 0, r.stream>>>(g.off.p, g.n, mx.p); launched();
-        const int64_t D = mx.get(0), W = (D + 31) >> 5;
-        if ((size_t)(D + D * W) * 4 <= r.smem_optin) {
+        const int D = mx.get(0);
+        if (matrix_words(D) * 4 + 28 * 1024 <= r.smem_optin) {
             *out = count_on_dag(g.n, g.slots, g.off.p, g.nbr.p, k);
             return;
         }
