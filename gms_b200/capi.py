@@ -82,6 +82,7 @@ SIGNATURES = {
     "gmsb_pair_similarity": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, _i32p, _i32p, _f64p]),
     "gmsb_edge_similarity": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int64)]),
     "gmsb_kclique_count": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]),
+    "gmsb_kclique_count_ex": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64)]),
     "gmsb_kclique_count_ordered": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]),
 }
 
@@ -304,9 +305,9 @@ class Graph:
         return out[:m.value]
 
     # --- cliques
-    def kclique_count(self, k):
+    def kclique_count(self, k, part_index=0, part_count=1):
         out = C.c_uint64(0)
-        _check(lib().gmsb_kclique_count(self.h, k, C.byref(out)))
+        _check(lib().gmsb_kclique_count_ex(self.h, k, part_index, part_count, C.byref(out)))
         return out.value
 
     def kclique_count_ordered(self, k):

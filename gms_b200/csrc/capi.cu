@@ -346,6 +346,12 @@ GMSB_API int gmsb_kclique_count(gmsb_graph_t g, int k, uint64_t *out) {
         kclique_count(G(g), k, out);
     });
 }
+GMSB_API int gmsb_kclique_count_ex(gmsb_graph_t g, int k, int part_index, int part_count, uint64_t *out) {
+    return guarded([&] {
+        GMSB_REQUIRE(out && k >= 1, "kclique_count: bad arguments");
+        kclique_count(G(g), k, out, part_index, part_count <= 0 ? 1 : part_count);
+    });
+}
 GMSB_API int gmsb_kclique_count_ordered(gmsb_graph_t g, int k, uint64_t *out) {
     return guarded([&] {
         GMSB_REQUIRE(out && k >= 1, "kclique_count_ordered: bad arguments");

@@ -61,7 +61,7 @@ __device__ __forceinline__ unsigned long long dfs32(const uint32_t *rows, uint32
 
 __global__ void __launch_bounds__(256)
 k_kclique_small(const vid_t *__restrict__ verts, int64_t count, const eid_t *__restrict__ off,
-                const vid_t *__restrict__ nbr, int k, unsigned long long *__restrict__ total) {
+                const vid_t *__restrict__ nbr, int k, unsigned long long *__restrict__ total, int pi, int P) {
     __shared__ uint32_t rows_s[8][32];
     __shared__ unsigned long long red[8];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -69,7 +69,7 @@ k_kclique_small(const vid_t *__restrict__ verts, int64_t count, const eid_t *__r
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     uint32_t *rows = rows_s[wib];
     unsigned long long acc = 0;
-    for (int64_t t = warp; t < count; t += nwarps) {
+    for (int64_t t = pi + warp * P; t < count; t += nwarps * P) {
         const vid_t u = verts[t];
         const eid_t ob = off[u];
         const int D = (int)(off[u + 1] - ob);                 // <= 32
@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
 k_kclique_big(const vid_t *__restrict__ verts, const int64_t *__restrict__ item_base, int64_t nverts, int64_t count,
               const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, int k, int maxD,
               unsigned long long *__restrict__ total, unsigned int *__restrict__ ticket,
-              uint32_t *__restrict__ spill) {
+              uint32_t *__restrict__ spill, int pi, int P) {
     extern __shared__ uint32_t smem[];
     // member list + bit matrix live in shared memory, or — when max d+ makes them larger than an SM's shared
     // memory — in this CTA's slice of a global scratch buffer (L2-resident for the sizes that occur)
@@ -355,7 +355,7 @@ k_kclique_big(const vid_t *__restrict__ verts, const int64_t *__restrict__ item_
         __syncthreads();
         if (tid == 0) { s_item = atomicAdd(ticket, 1u); s_next = 0; }
         __syncthreads();
-        const int64_t item = (int64_t)s_item;
+        const int64_t item = pi + (int64_t)s_item * P;          // this process's share: items pi, pi+P, ...
         if (item >= count) break;
         // item -> (vertex t, part of its second-level members): heavy vertices are cut into several items so that
         // one dense neighbourhood does not serialise on a single CTA (item_base = exclusive scan of parts)
@@ -456,10 +456,10 @@ __global__ void k_key_vertex(const uint64_t *__restrict__ keys, int64_t cnt, vid
         verts[i] = (vid_t)(uint32_t)keys[i];
 }
 
-uint64_t count_on_dag(int64_t n, int64_t m, const eid_t *off, const vid_t *nbr, int k) {
+uint64_t count_on_dag(int64_t n, int64_t m, const eid_t *off, const vid_t *nbr, int k, int pi, int P) {
     Runtime &r = rt();
-    if (k == 1) return (uint64_t)n;                // parallelize.h:43
-    if (k == 2) return (uint64_t)m;                // parallelize.h:44
+    if (k == 1) return pi == 0 ? (uint64_t)n : 0;  // parallelize.h:43
+    if (k == 2) return pi == 0 ? (uint64_t)m : 0;  // parallelize.h:44
     GMSB_REQUIRE(k <= kMaxK, "kclique_count: clique size above 16 is not supported");
     if (n == 0 || m == 0) return 0;
     DevBuf<uint8_t> fs(n), fb(n);
@@ -477,7 +477,7 @@ uint64_t count_on_dag(int64_t n, int64_t m, const eid_t *off, const vid_t *nbr, 
         DevBuf<vid_t> vs(ns);
         k_bucket_fill<<<grid_for(n, 256), 256, 0, r.stream>>>(n, fs.p, ps.p, vs.p); launched();
         int grid = (int)std::min<int64_t>(ceil_div(ns, 8), (int64_t)r.sm_count * 16);
-        k_kclique_small<<<grid, 256, 0, r.stream>>>(vs.p, ns, off, nbr, k, total.p); launched();
+        k_kclique_small<<<grid, 256, 0, r.stream>>>(vs.p, ns, off, nbr, k, total.p, pi, P); launched();
     }
     if (nb) {
         DevBuf<vid_t> vb(nb);
@@ -517,7 +517,7 @@ uint64_t count_on_dag(int64_t n, int64_t m, const eid_t *off, const vid_t *nbr, 
                 const int grid = (int)std::min<int64_t>(n_items, (int64_t)r.sm_count * resident);
                 if (!in_smem) spill.alloc((size_t)grid * (need / 4));
                 kern<<<grid, block, smem, r.stream>>>(vb.p + first, item_base.p, cnt, n_items, off, nbr, k, classD,
-                                                          total.p, ticket.p, in_smem ? nullptr : spill.p);
+                                                          total.p, ticket.p, in_smem ? nullptr : spill.p, pi, P);
                 launched();
                 GMSB_CUDA(cudaStreamSynchronize(r.stream));
             };
@@ -556,16 +556,23 @@ __global__ void k_max_out(const eid_t *__restrict__ off, int64_t n, int *out) {
 }
 }  // namespace
 
-void kclique_count(Graph &g, int k, uint64_t *out) {
+// part_index / part_count: this process counts share part_index of part_count of the per-vertex sub-problems
+// (multi-GPU: graph replicated, sub-problems dealt out round-robin in descending-size order, counts summed by the
+// caller with one all-reduce); the shares add up to the full count.
+void kclique_count(Graph &g, int k, uint64_t *out, int pi, int P) {
+    GMSB_REQUIRE(P >= 1 && pi >= 0 && pi < P, "kclique_count: bad partition");
     if (g.directed) {
         Runtime &r = rt();
-        if (k <= 2 || g.n == 0 || g.slots == 0) { *out = count_on_dag(g.n, g.slots, g.off.p, g.nbr.p, k); return; }
+        if (k <= 2 || g.n == 0 || g.slots == 0) {
+            *out = count_on_dag(g.n, g.slots, g.off.p, g.nbr.p, k, pi, P);
+            return;
+        }
         DevBuf<int> mx(1);
         mx.zero();
         k_max_out<<<grid_for(g.n, 256), 256, 0, r.stream>>>(g.off.p, g.n, mx.p); launched();
         const int D = mx.get(0);
         if (matrix_words(D) * 4 + 28 * 1024 <= r.smem_optin) {
-            *out = count_on_dag(g.n, g.slots, g.off.p, g.nbr.p, k);
+            *out = count_on_dag(g.n, g.slots, g.off.p, g.nbr.p, k, pi, P);
             return;
         }
         // The reference's own degeneracy pipeline orients from later- to earlier-removed vertices, which leaves
@@ -576,14 +583,14 @@ void kclique_count(Graph &g, int k, uint64_t *out) {
         Graph *und = graph_from_edgelist_device(g.slots, src.p, g.nbr.p, true);
         try {
             und->dag = build_degree_dag(*und);
-            *out = count_on_dag(und->dag->n, und->dag->m, und->dag->off.p, und->dag->nbr.p, k);
+            *out = count_on_dag(und->dag->n, und->dag->m, und->dag->off.p, und->dag->nbr.p, k, pi, P);
         } catch (...) { delete und; throw; }
         delete und;
         return;
     }
-    if (k == 1) { *out = (uint64_t)g.n; return; }
+    if (k == 1) { *out = pi == 0 ? (uint64_t)g.n : 0; return; }
     if (!g.dag) g.dag = build_degree_dag(g);
-    *out = count_on_dag(g.dag->n, g.dag->m, g.dag->off.p, g.dag->nbr.p, k);
+    *out = count_on_dag(g.dag->n, g.dag->m, g.dag->off.p, g.dag->nbr.p, k, pi, P);
 }
 
 // CliqueCount on the unoriented graph counts ordered tuples: k! * C_k, with size_t wrap-around.

@@ -24,7 +24,7 @@ void degeneracy_rank(Graph &g, vid_t *out_rank);
 void degeneracy_order_approx(Graph &g, double epsilon, bool rank_format, vid_t *out_host);
 
 // kclique.cu
-void kclique_count(Graph &g, int k, uint64_t *out);
+void kclique_count(Graph &g, int k, uint64_t *out, int part_index = 0, int part_count = 1);
 void kclique_count_ordered(Graph &g, int k, uint64_t *out);
 
 }  // namespace gmsb

@@ -173,6 +173,9 @@ GMSB_API int gmsb_edge_similarity(gmsb_graph_t g, int metric, double *out, int64
  * g may be a DAG from gmsb_orient, or an undirected graph (then it is degree-oriented internally; the count is
  * orientation-invariant). k==1 -> nodes, k==2 -> edges as parallelize.h:43-44. */
 GMSB_API int gmsb_kclique_count(gmsb_graph_t g, int k, uint64_t *out);
+/* multi-GPU form: this process counts share part_index of part_count of the per-vertex sub-problems (graph
+ * replicated, dealt out round-robin in descending size); the shares add up to gmsb_kclique_count's result. */
+GMSB_API int gmsb_kclique_count_ex(gmsb_graph_t g, int k, int part_index, int part_count, uint64_t *out);
 /* CliqueCount<Set,SGraph,Set2> (returns k!*C_k)           gms/algorithms/set_based/k_clique_count/k_clique_count_set_based.h:20-31 */
 GMSB_API int gmsb_kclique_count_ordered(gmsb_graph_t g, int k, uint64_t *out);
 
