@@ -22,6 +22,9 @@
 #include "isect.cuh"
 #include "orient.cuh"
 #include "ops.cuh"
+#include "kclique_lane.cuh"
+#include <cstdlib>
+#include <cstring>
 
 namespace gmsb {
 
@@ -439,7 +442,7 @@ __global__ void k_degree_key(const vid_t *__restrict__ verts, int64_t cnt, const
 // parts[t] = number of work items vertex t is cut into; also counts the vertices above the mid-size class
 constexpr int kMidD = 512;
 __global__ void k_parts(const vid_t *__restrict__ verts, int64_t cnt, const eid_t *__restrict__ off,
-                        int k, int64_t *__restrict__ parts, int *__restrict__ nhuge) {
+                        int k, int part_rows, int64_t *__restrict__ parts, int *__restrict__ nhuge) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i <= cnt; i += (int64_t)gridDim.x * blockDim.x) {
         if (i == cnt) { parts[i] = 0; continue; }
         const vid_t u = verts[i];
@@ -447,13 +450,38 @@ __global__ void k_parts(const vid_t *__restrict__ verts, int64_t cnt, const eid_
         // for k <= 4 building the matrix dominates, so a vertex stays whole; deeper searches are cut finer
         // (every part rebuilds the vertex's matrix, so parts are kept few: the split is only there to spread the
         // handful of densest neighbourhoods over several SMs)
-        parts[i] = k <= 4 ? 1 : (d > kMidD ? (d + 255) / 256 : 1);
+        parts[i] = k <= 4 ? 1 : (d > kMidD ? (d + part_rows - 1) / part_rows : 1);
         if (d > kMidD) atomicAdd(nhuge, 1);
     }
 }
 __global__ void k_key_vertex(const uint64_t *__restrict__ keys, int64_t cnt, vid_t *__restrict__ verts) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < cnt; i += (int64_t)gridDim.x * blockDim.x)
         verts[i] = (vid_t)(uint32_t)keys[i];
+}
+
+// number of vertices (of the descending-degree list) above each class boundary of the lane kernels
+__global__ void k_class_counts(const vid_t *__restrict__ verts, int64_t cnt, const eid_t *__restrict__ off,
+                               int *__restrict__ counts) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < cnt; i += (int64_t)gridDim.x * blockDim.x) {
+        const vid_t u = verts[i];
+        const int64_t d = off[u + 1] - off[u];
+        if (d > 512) atomicAdd(&counts[0], 1);
+        if (d > 256) atomicAdd(&counts[1], 1);
+        if (d > 128) atomicAdd(&counts[2], 1);
+        if (d > 64) atomicAdd(&counts[3], 1);
+    }
+}
+
+// Which kernels run the d+ > 32 sub-problems: the lane-parallel ones (kclique_lane.cuh) or the warp-cooperative ones
+// above.  GMSB_KCLIQUE_IMPL=warp|lane forces one family (A/B measurements, tests); the default takes the lane
+// kernels where they are faster (measured on B200) and supported (4 <= k <= 10).
+constexpr int kLaneMinK = 5;
+bool use_lane_kernels(int k) {
+    const char *e = std::getenv("GMSB_KCLIQUE_IMPL");
+    if (e && !std::strcmp(e, "warp")) return false;
+    if (k < 4 || k - 1 > lane::kMaxNeed) return false;
+    if (e && !std::strcmp(e, "lane")) return true;
+    return k >= kLaneMinK;
 }
 
 uint64_t count_on_dag(int64_t n, int64_t m, const eid_t *off, const vid_t *nbr, int k, int pi, int P) {
@@ -489,11 +517,12 @@ uint64_t count_on_dag(int64_t n, int64_t m, const eid_t *off, const vid_t *nbr, 
         if (row_words(maxD) > 128)
             throw Error(GMSB_ERR_UNSUPPORTED, "kclique_count: max out-degree " + std::to_string(maxD) +
                                                   " exceeds 4096; orient by degree or degeneracy first");
+        const bool lane_path = use_lane_kernels(k);
         // work items: (vertex, interleaved part of its second-level members)
         DevBuf<int64_t> parts(nb + 1), item_base(nb + 1);
         DevBuf<int> nhuge(1);
         nhuge.zero();
-        k_parts<<<grid_for(nb, 256), 256, 0, r.stream>>>(vb.p, nb, off, k, parts.p, nhuge.p); launched();
+        k_parts<<<grid_for(nb, 256), 256, 0, r.stream>>>(vb.p, nb, off, k, lane_path ? 64 : 256, parts.p, nhuge.p); launched();
         const int64_t n_huge = nhuge.get(0);           // vertices with d+ > kMidD come first (sorted descending)
         // two launches so that the many mid-size neighbourhoods get a small matrix and several CTAs per SM
         auto run_class = [&](int64_t first, int64_t cnt, int classD, bool huge) {
@@ -531,8 +560,48 @@ uint64_t count_on_dag(int64_t n, int64_t m, const eid_t *off, const vid_t *nbr, 
                 launch(k_kclique_big<1, 512, 2>, 512);        // kMidD = 512 -> W = 16
             }
         };
-        run_class(0, n_huge, maxD, true);
-        run_class(n_huge, nb - n_huge, kMidD, false);
+        if (lane_path) {
+            DevBuf<int> cc(4);
+            cc.zero();
+            k_class_counts<<<grid_for(nb, 256), 256, 0, r.stream>>>(vb.p, nb, off, cc.p); launched();
+            int bound[4];
+            cc.download(bound, 4);
+            DevBuf<unsigned int> tickets(5);
+            tickets.zero();
+            DevBuf<lane::u64> spill;
+            if (n_huge) {           // d+ > 512: CTA-wide top of the tree, compact matrices below
+                exclusive_sum(parts.p, item_base.p, n_huge + 1);
+                const int64_t n_items = item_base.get(n_huge);
+                const size_t full = lane::huge_smem_words(maxD, true) * 8;
+                const bool in_smem = full + 2048 <= r.smem_optin;
+                const size_t smem = in_smem ? full : lane::huge_smem_words(maxD, false) * 8;
+                GMSB_CUDA(cudaFuncSetAttribute(lane::k_kclique_lane_huge, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)smem));
+                const int grid = (int)std::min<int64_t>(n_items, (int64_t)r.sm_count);
+                if (!in_smem) spill.alloc((size_t)grid * (size_t)maxD * (size_t)lane::huge_pitch(maxD));
+                lane::k_kclique_lane_huge<<<grid, lane::kHugeBlock, smem, r.stream>>>(
+                    vb.p, item_base.p, n_huge, n_items, off, nbr, k, maxD, total.p, tickets.p,
+                    in_smem ? nullptr : spill.p, pi, P);
+                launched();
+            }
+            auto mid = [&](auto kern, int block, int64_t first, int64_t cnt, unsigned int *ticket) {
+                if (cnt <= 0) return;
+                int resident = 0;
+                GMSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, block, 0));
+                GMSB_REQUIRE(resident >= 1, "kclique_count: kernel does not fit on an SM");
+                const int grid = (int)std::min<int64_t>(cnt, (int64_t)r.sm_count * resident);
+                kern<<<grid, block, 0, r.stream>>>(vb.p + first, cnt, off, nbr, k, total.p, ticket, pi, P);
+                launched();
+            };
+            mid(lane::k_kclique_lane_mid<8, 512, 1>, 512, bound[0], bound[1] - bound[0], tickets.p + 1);
+            mid(lane::k_kclique_lane_mid<4, 256, 3>, 256, bound[1], bound[2] - bound[1], tickets.p + 2);
+            mid(lane::k_kclique_lane_mid<2, 128, 8>, 128, bound[2], bound[3] - bound[2], tickets.p + 3);
+            mid(lane::k_kclique_lane_mid<1, 128, 8>, 128, bound[3], nb - bound[3], tickets.p + 4);
+            GMSB_CUDA(cudaStreamSynchronize(r.stream));
+        } else {
+            run_class(0, n_huge, maxD, true);
+            run_class(n_huge, nb - n_huge, kMidD, false);
+        }
     }
     return total.get(0);
 }

@@ -1,0 +1,215 @@
+// kclique_lane_core.cuh — the per-lane part of the k-clique search (host/device, no warp primitives).
+//
+// Replaces the inner recursion of KClique::KcListing::listing (gms/algorithms/non_set_based/k_clique_list/kernels/
+// kclisting.h:92-114): there a recursion level relabels and swaps adjacency entries and the last level counts one
+// clique at a time; here a sub-problem is a COMPACT bit matrix (c <= 512 members, row a = members after a that are
+// adjacent to a) and every GPU lane runs its own depth-first search over it with the candidate sets held in
+// registers.  A level is one AND of NW 64-bit words, the last two levels are one pass of AND + popcount.
+//
+// The functions are __host__ __device__ so that tests/cpp/lane_core_test.cpp can run exactly this code on the CPU
+// against a brute-force count (the container that builds the library has no GPU).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define GMSB_HD __host__ __device__ __forceinline__
+#else
+#define GMSB_HD inline
+#endif
+
+namespace gmsb {
+namespace lane {
+
+using u64 = unsigned long long;
+
+constexpr int kCMax = 512;         // members of a compact sub-problem (9-bit member indices)
+constexpr int kPathBits = 9;
+constexpr int kPathLevels = 7;     // 7 x 9 bits in one 64-bit register
+constexpr int kMaxNeed = kPathLevels + 2;   // deepest stored level is need - 3
+
+GMSB_HD int popc64(u64 x) {
+#if defined(__CUDA_ARCH__)
+    return __popcll(x);
+#else
+    return __builtin_popcountll(x);
+#endif
+}
+GMSB_HD int ctz64(u64 x) {     // x != 0
+#if defined(__CUDA_ARCH__)
+    return __ffsll((long long)x) - 1;
+#else
+    return __builtin_ctzll(x);
+#endif
+}
+
+// pitch (64-bit words per row) of a compact matrix with NW valid words per row: odd, so that lanes reading the same
+// word of 32 different rows spread over the shared-memory banks
+GMSB_HD constexpr int pitch_for(int nw) { return nw | 1; }
+
+// bits b of a 64-bit word with (b mod 2^split_log2) == s: the second clique vertex of a task is restricted to one
+// residue class, which cuts a member's subtree into 2^split_log2 independent tasks without any index arithmetic
+GMSB_HD u64 stripe_mask(int split_log2, int s) {
+    u64 rep;
+    switch (split_log2) {
+        case 0: rep = ~0ull; break;
+        case 1: rep = 0x5555555555555555ull; break;
+        case 2: rep = 0x1111111111111111ull; break;
+        case 3: rep = 0x0101010101010101ull; break;
+        case 4: rep = 0x0001000100010001ull; break;
+        case 5: rep = 0x0000000100000001ull; break;
+        default: rep = 1ull; break;
+    }
+    return rep << s;
+}
+
+// bits of word w (bit positions 64w .. 64w+63) whose position is greater than `pos`
+GMSB_HD u64 above_mask(int w, int pos) {
+    const int rel = pos - (w << 6);
+    if (rel < 0) return ~0ull;
+    if (rel >= 63) return 0ull;
+    return ~0ull << (rel + 1);
+}
+
+template <int NW>
+struct LaneState {
+    u64 cur[NW];      // candidate set at the current level
+    u64 it[NW];       // members of cur not yet tried at this level
+    u64 path;         // kPathBits-bit fields: [0] = first member, [l] = member picked at level l-1
+    u64 stripe;       // residue-class mask applied to the picks of level 0
+    int level;        // -1 = idle
+};
+
+// task = (first member a, residue class of the second member)
+template <int NW>
+GMSB_HD void lane_begin(LaneState<NW> &s, const u64 *cm, int pitch, unsigned task, int split_log2) {
+    const int a = (int)(task >> split_log2);
+    s.stripe = stripe_mask(split_log2, (int)(task & ((1u << split_log2) - 1u)));
+    const u64 *row = cm + (size_t)a * pitch;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        s.cur[w] = row[w];
+        s.it[w] = row[w] & s.stripe;
+    }
+    s.level = 0;
+    s.path = (u64)a;
+}
+
+// Walks the search tree of the lane's task until it reaches a candidate set Q with exactly two vertices left to
+// pick (returns true; the caller counts the pairs inside Q) or the task is finished (returns false, level = -1).
+// need >= 4: size of the cliques counted inside the compact graph (the first member is one of them).
+template <int NW>
+GMSB_HD bool lane_advance(LaneState<NW> &s, const u64 *cm, int pitch, int need, u64 (&Q)[NW]) {
+    for (;;) {
+        int v = -1;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            if (v < 0 && s.it[w]) {
+                v = (w << 6) + ctz64(s.it[w]);
+                s.it[w] &= s.it[w] - 1;
+            }
+        }
+        if (v < 0) {
+            if (s.level == 0) { s.level = -1; return false; }
+            // back to the parent: its candidate set is the AND of the rows on the path (nothing but the path is
+            // stored per level, so the search needs no per-lane stack memory)
+            const int child = (int)((s.path >> (kPathBits * s.level)) & (kCMax - 1));
+            --s.level;
+            const u64 *r0 = cm + (size_t)(s.path & (kCMax - 1)) * pitch;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) s.cur[w] = r0[w];
+            for (int t = 1; t <= s.level; ++t) {
+                const u64 *r = cm + (size_t)((s.path >> (kPathBits * t)) & (kCMax - 1)) * pitch;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) s.cur[w] &= r[w];
+            }
+#pragma unroll
+            for (int w = 0; w < NW; ++w) s.it[w] = s.cur[w] & above_mask(w, child);
+            if (s.level == 0) {
+#pragma unroll
+                for (int w = 0; w < NW; ++w) s.it[w] &= s.stripe;
+            }
+            continue;
+        }
+        const u64 *row = cm + (size_t)v * pitch;
+        int pc = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            Q[w] = s.cur[w] & row[w];
+            pc += popc64(Q[w]);
+        }
+        const int left = need - s.level - 2;         // vertices still to pick after v
+        if (left == 2) {
+            if (pc >= 2) return true;
+        } else if (pc >= left) {
+            ++s.level;
+            const int sh = kPathBits * s.level;
+            s.path = (s.path & ~((u64)(kCMax - 1) << sh)) | ((u64)v << sh);
+#pragma unroll
+            for (int w = 0; w < NW; ++w) { s.cur[w] = Q[w]; s.it[w] = Q[w]; }
+        }
+    }
+}
+
+// sum over x in I of |A ∩ row(x)|: the last two clique vertices in one pass (row(x) only has members after x)
+template <int NW>
+GMSB_HD unsigned leaf_pairs(const u64 *cm, int pitch, const u64 (&I)[NW], const u64 (&A)[NW]) {
+    unsigned cnt = 0;
+#pragma unroll
+    for (int w1 = 0; w1 < NW; ++w1) {
+        u64 bits = I[w1];
+        while (bits) {
+            const int x = (w1 << 6) + ctz64(bits);
+            bits &= bits - 1;
+            const u64 *row = cm + (size_t)x * pitch;
+#pragma unroll
+            for (int w = w1; w < NW; ++w) cnt += (unsigned)popc64(A[w] & row[w]);
+        }
+    }
+    return cnt;
+}
+
+// whole task on one lane (the CPU test and the GPU lanes run the same sequence of calls)
+template <int NW>
+GMSB_HD u64 lane_run_task(const u64 *cm, int pitch, int need, unsigned task, int split_log2) {
+    LaneState<NW> s;
+    lane_begin<NW>(s, cm, pitch, task, split_log2);
+    if (need == 3) return leaf_pairs<NW>(cm, pitch, s.it, s.cur);
+    u64 total = 0, Q[NW];
+    while (lane_advance<NW>(s, cm, pitch, need, Q)) total += leaf_pairs<NW>(cm, pitch, Q, Q);
+    return total;
+}
+
+// ---- compaction of a candidate set of a big matrix into a compact matrix -------------------------------------------
+// set: P1 words over the positions of the big matrix; prefix[w] = members in words < w
+GMSB_HD int compact_index(const u64 *set, const int *prefix, int p) {
+    const int w = p >> 6;
+    return prefix[w] + popc64(set[w] & ((1ull << (p & 63)) - 1ull));
+}
+
+// compact row of the member at position pa (big row `row`, W1 valid words): bit idx(q) for every member q in the row
+GMSB_HD void compact_row(const u64 *set, const int *prefix, int W1, const u64 *row, int pa, u64 *out, int nwb) {
+    for (int w2 = 0; w2 < nwb; ++w2) out[w2] = 0ull;
+    int curw = -1;
+    u64 acc = 0;
+    for (int w = pa >> 6; w < W1; ++w) {
+        const u64 sw = set[w];
+        u64 x = row[w] & sw;
+        const int base = prefix[w];
+        while (x) {
+            const int b = ctz64(x);
+            x &= x - 1;
+            const int idx = base + popc64(sw & ((1ull << b) - 1ull));
+            if ((idx >> 6) != curw) {
+                if (curw >= 0) out[curw] = acc;
+                curw = idx >> 6;
+                acc = 0;
+            }
+            acc |= 1ull << (idx & 63);
+        }
+    }
+    if (curw >= 0) out[curw] = acc;
+}
+
+}  // namespace lane
+}  // namespace gmsb
