@@ -569,21 +569,37 @@ uint64_t count_on_dag(int64_t n, int64_t m, const eid_t *off, const vid_t *nbr, 
             DevBuf<unsigned int> tickets(5);
             tickets.zero();
             DevBuf<lane::u64> spill;
+            // GMSB_KCLIQUE_TRACE=1: device time of every class launch on stderr (profiling aid)
+            const bool trace = std::getenv("GMSB_KCLIQUE_TRACE") != nullptr;
+            cudaEvent_t ev[6] = {};
+            int nev = 0;
+            auto mark = [&]() {
+                if (!trace) return;
+                cudaEventCreate(&ev[nev]);
+                cudaEventRecord(ev[nev++], r.stream);
+            };
+            mark();
             if (n_huge) {           // d+ > 512: CTA-wide top of the tree, compact matrices below
                 exclusive_sum(parts.p, item_base.p, n_huge + 1);
                 const int64_t n_items = item_base.get(n_huge);
                 const size_t full = lane::huge_smem_words(maxD, true) * 8;
                 const bool in_smem = full + 2048 <= r.smem_optin;
                 const size_t smem = in_smem ? full : lane::huge_smem_words(maxD, false) * 8;
-                GMSB_CUDA(cudaFuncSetAttribute(lane::k_kclique_lane_huge, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)smem));
-                const int grid = (int)std::min<int64_t>(n_items, (int64_t)r.sm_count);
-                if (!in_smem) spill.alloc((size_t)grid * (size_t)maxD * (size_t)lane::huge_pitch(maxD));
-                lane::k_kclique_lane_huge<<<grid, lane::kHugeBlock, smem, r.stream>>>(
-                    vb.p, item_base.p, n_huge, n_items, off, nbr, k, maxD, total.p, tickets.p,
-                    in_smem ? nullptr : spill.p, pi, P);
-                launched();
+                auto launch_huge = [&](auto kern, int block) {
+                    GMSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    const int grid = (int)std::min<int64_t>(n_items, (int64_t)r.sm_count);
+                    if (!in_smem) spill.alloc((size_t)grid * (size_t)maxD * (size_t)lane::huge_pitch(maxD));
+                    kern<<<grid, block, smem, r.stream>>>(vb.p, item_base.p, n_huge, n_items, off, nbr, k, maxD, total.p,
+                                                          tickets.p, in_smem ? nullptr : spill.p, pi, P);
+                    launched();
+                };
+                // 512 threads cap the kernel at 128 registers and it spills; 384 threads (168 registers, no spills) were
+                // 6 % faster at scale 22, k = 6.  GMSB_KCLIQUE_HUGE_BLOCK=512 selects the other build for A/B runs.
+                const char *hb = std::getenv("GMSB_KCLIQUE_HUGE_BLOCK");
+                if (hb && std::atoi(hb) == 512) launch_huge(lane::k_kclique_lane_huge<512>, 512);
+                else launch_huge(lane::k_kclique_lane_huge<384>, 384);
             }
+            mark();
             auto mid = [&](auto kern, int block, int64_t first, int64_t cnt, unsigned int *ticket) {
                 if (cnt <= 0) return;
                 int resident = 0;
@@ -593,11 +609,27 @@ uint64_t count_on_dag(int64_t n, int64_t m, const eid_t *off, const vid_t *nbr, 
                 kern<<<grid, block, 0, r.stream>>>(vb.p + first, cnt, off, nbr, k, total.p, ticket, pi, P);
                 launched();
             };
-            mid(lane::k_kclique_lane_mid<8, 512, 1>, 512, bound[0], bound[1] - bound[0], tickets.p + 1);
-            mid(lane::k_kclique_lane_mid<4, 256, 3>, 256, bound[1], bound[2] - bound[1], tickets.p + 2);
-            mid(lane::k_kclique_lane_mid<2, 128, 8>, 128, bound[2], bound[3] - bound[2], tickets.p + 3);
-            mid(lane::k_kclique_lane_mid<1, 128, 8>, 128, bound[3], nb - bound[3], tickets.p + 4);
+            auto mid_marked = [&](auto kern, int block, int64_t first, int64_t cnt, unsigned int *ticket) {
+                mid(kern, block, first, cnt, ticket);
+                mark();
+            };
+            mid_marked(lane::k_kclique_lane_mid<8, 384, 2>, 384, bound[0], bound[1] - bound[0], tickets.p + 1);
+            mid_marked(lane::k_kclique_lane_mid<4, 256, 4>, 256, bound[1], bound[2] - bound[1], tickets.p + 2);
+            mid_marked(lane::k_kclique_lane_mid<2, 128, 8>, 128, bound[2], bound[3] - bound[2], tickets.p + 3);
+            mid_marked(lane::k_kclique_lane_mid<1, 128, 8>, 128, bound[3], nb - bound[3], tickets.p + 4);
             GMSB_CUDA(cudaStreamSynchronize(r.stream));
+            if (trace) {
+                static const char *names[5] = {"huge(d+>512)", "mid8(<=512)", "mid4(<=256)", "mid2(<=128)", "mid1(<=64)"};
+                const int64_t counts[5] = {n_huge, bound[1] - bound[0], bound[2] - bound[1], bound[3] - bound[2],
+                                           nb - bound[3]};
+                for (int i = 0; i + 1 < nev; ++i) {
+                    float ms = 0;
+                    cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+                    std::fprintf(stderr, "[gmsb kclique k=%d] %-13s vertices=%lld ms=%.3f\n", k, names[i],
+                                 (long long)counts[i], ms);
+                }
+                for (int i = 0; i < nev; ++i) cudaEventDestroy(ev[i]);
+            }
         } else {
             run_class(0, n_huge, maxD, true);
             run_class(n_huge, nb - n_huge, kMidD, false);

@@ -48,11 +48,13 @@ __device__ u64 lane_tasks(const u64 *cm, int pitch, int c, int need, int split_l
         }
         if (__all_sync(0xffffffffu, s.level < 0)) break;
         if (s.level >= 0) {
+            u64 Q[NW];
             if (need == 3) {
-                total += leaf_pairs<NW>(cm, pitch, s.it, s.cur);
+#pragma unroll
+                for (int w = 0; w < NW; ++w) Q[w] = s.cur[w] & s.stripe;
+                total += leaf_pairs<NW>(cm, pitch, Q, s.cur);
                 s.level = -1;
             } else {
-                u64 Q[NW];
                 if (lane_advance<NW>(s, cm, pitch, need, Q)) total += leaf_pairs<NW>(cm, pitch, Q, Q);
             }
         }
@@ -124,7 +126,6 @@ k_kclique_lane_mid(const vid_t *__restrict__ verts, int64_t count, const eid_t *
 }
 
 // ---- d+ > 512 ---------------------------------------------------------------------------------------------------------
-constexpr int kHugeBlock = 512;
 constexpr int kStackLevels = 16;
 
 __host__ __device__ inline int huge_pitch(int maxD) { return ((maxD + 63) >> 6) | 1; }
@@ -135,12 +136,12 @@ __host__ __device__ inline size_t huge_smem_words(int maxD, bool matrix_in_smem)
            (size_t)((maxD + 1) >> 1) + ((P1 + 2) >> 1) + (size_t)(kCMax / 4);
 }
 
-__global__ void __launch_bounds__(kHugeBlock, 1)
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK, 1)
 k_kclique_lane_huge(const vid_t *__restrict__ verts, const int64_t *__restrict__ item_base, int64_t nverts,
                     int64_t count, const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, int k, int maxD,
                     unsigned long long *__restrict__ total, unsigned int *__restrict__ ticket,
                     u64 *__restrict__ spill, int pi, int P) {
-    constexpr int BLOCK = kHugeBlock;
     extern __shared__ u64 smem64[];
     const int P1 = huge_pitch(maxD);
     u64 *M1 = spill ? spill + (size_t)blockIdx.x * ((size_t)maxD * P1) : smem64;
@@ -234,8 +235,7 @@ k_kclique_lane_huge(const vid_t *__restrict__ verts, const int64_t *__restrict__
                                 if ((set[p >> 6] >> (p & 63)) & 1ull)
                                     list[compact_index(set, prefix, p)] = (unsigned short)p;
                             __syncthreads();
-                            const int nw = (c + 63) >> 6;
-                            const int nwb = nw <= 1 ? 1 : nw <= 2 ? 2 : nw <= 4 ? 4 : 8;
+                            const int nwb = (c + 63) >> 6;         // 1..8 words per compact row
                             const int pitch2 = pitch_for(nwb);
                             for (int a = tid; a < c; a += BLOCK) {
                                 const int pa = list[a];
@@ -246,7 +246,11 @@ k_kclique_lane_huge(const vid_t *__restrict__ verts, const int64_t *__restrict__
                             switch (nwb) {
                                 case 1: acc += lane_tasks<1>(M2, pitch2, c, need, sl, &s_counter, lane); break;
                                 case 2: acc += lane_tasks<2>(M2, pitch2, c, need, sl, &s_counter, lane); break;
+                                case 3: acc += lane_tasks<3>(M2, pitch2, c, need, sl, &s_counter, lane); break;
                                 case 4: acc += lane_tasks<4>(M2, pitch2, c, need, sl, &s_counter, lane); break;
+                                case 5: acc += lane_tasks<5>(M2, pitch2, c, need, sl, &s_counter, lane); break;
+                                case 6: acc += lane_tasks<6>(M2, pitch2, c, need, sl, &s_counter, lane); break;
+                                case 7: acc += lane_tasks<7>(M2, pitch2, c, need, sl, &s_counter, lane); break;
                                 default: acc += lane_tasks<8>(M2, pitch2, c, need, sl, &s_counter, lane); break;
                             }
                         } else {

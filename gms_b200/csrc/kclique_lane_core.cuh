@@ -74,9 +74,9 @@ GMSB_HD u64 above_mask(int w, int pos) {
 template <int NW>
 struct LaneState {
     u64 cur[NW];      // candidate set at the current level
-    u64 it[NW];       // members of cur not yet tried at this level
     u64 path;         // kPathBits-bit fields: [0] = first member, [l] = member picked at level l-1
     u64 stripe;       // residue-class mask applied to the picks of level 0
+    int pos;          // last member tried at the current level (members are tried in ascending order)
     int level;        // -1 = idle
 };
 
@@ -87,33 +87,31 @@ GMSB_HD void lane_begin(LaneState<NW> &s, const u64 *cm, int pitch, unsigned tas
     s.stripe = stripe_mask(split_log2, (int)(task & ((1u << split_log2) - 1u)));
     const u64 *row = cm + (size_t)a * pitch;
 #pragma unroll
-    for (int w = 0; w < NW; ++w) {
-        s.cur[w] = row[w];
-        s.it[w] = row[w] & s.stripe;
-    }
+    for (int w = 0; w < NW; ++w) s.cur[w] = row[w];
     s.level = 0;
+    s.pos = a;                 // row a only has members after a
     s.path = (u64)a;
 }
 
 // Walks the search tree of the lane's task until it reaches a candidate set Q with exactly two vertices left to
 // pick (returns true; the caller counts the pairs inside Q) or the task is finished (returns false, level = -1).
 // need >= 4: size of the cliques counted inside the compact graph (the first member is one of them).
+// Per level only the picked member is remembered (in `path`); the parent's candidate set is recomputed from the
+// rows on the path on the way back, so the search needs no per-lane stack memory.
 template <int NW>
 GMSB_HD bool lane_advance(LaneState<NW> &s, const u64 *cm, int pitch, int need, u64 (&Q)[NW]) {
     for (;;) {
+        // next member of cur after pos (level 0: inside the task's residue class)
+        const u64 sm = s.level == 0 ? s.stripe : ~0ull;
         int v = -1;
 #pragma unroll
-        for (int w = 0; w < NW; ++w) {
-            if (v < 0 && s.it[w]) {
-                v = (w << 6) + ctz64(s.it[w]);
-                s.it[w] &= s.it[w] - 1;
-            }
+        for (int w = NW - 1; w >= 0; --w) {
+            const u64 m = s.cur[w] & sm & above_mask(w, s.pos);
+            if (m) v = (w << 6) + ctz64(m);
         }
         if (v < 0) {
             if (s.level == 0) { s.level = -1; return false; }
-            // back to the parent: its candidate set is the AND of the rows on the path (nothing but the path is
-            // stored per level, so the search needs no per-lane stack memory)
-            const int child = (int)((s.path >> (kPathBits * s.level)) & (kCMax - 1));
+            s.pos = (int)((s.path >> (kPathBits * s.level)) & (kCMax - 1));     // resume after the child just left
             --s.level;
             const u64 *r0 = cm + (size_t)(s.path & (kCMax - 1)) * pitch;
 #pragma unroll
@@ -123,14 +121,9 @@ GMSB_HD bool lane_advance(LaneState<NW> &s, const u64 *cm, int pitch, int need, 
 #pragma unroll
                 for (int w = 0; w < NW; ++w) s.cur[w] &= r[w];
             }
-#pragma unroll
-            for (int w = 0; w < NW; ++w) s.it[w] = s.cur[w] & above_mask(w, child);
-            if (s.level == 0) {
-#pragma unroll
-                for (int w = 0; w < NW; ++w) s.it[w] &= s.stripe;
-            }
             continue;
         }
+        s.pos = v;
         const u64 *row = cm + (size_t)v * pitch;
         int pc = 0;
 #pragma unroll
@@ -146,12 +139,15 @@ GMSB_HD bool lane_advance(LaneState<NW> &s, const u64 *cm, int pitch, int need, 
             const int sh = kPathBits * s.level;
             s.path = (s.path & ~((u64)(kCMax - 1) << sh)) | ((u64)v << sh);
 #pragma unroll
-            for (int w = 0; w < NW; ++w) { s.cur[w] = Q[w]; s.it[w] = Q[w]; }
+            for (int w = 0; w < NW; ++w) s.cur[w] = Q[w];
         }
     }
 }
 
-// sum over x in I of |A ∩ row(x)|: the last two clique vertices in one pass (row(x) only has members after x)
+// sum over x in I of |A ∩ row(x)|: the last two clique vertices in one pass (row(x) only has members after x, so
+// the words below x's own are skipped).  A variant that added the rows of seven members as bit planes (carry-save
+// adders, 3 popcounts per word instead of 7) was measured on B200 and was SLOWER (scale-22 k=6: 44 s vs 38 s): the
+// candidate sets this deep hold only 3-5 members per 64-bit word, so the groups were mostly padding.
 template <int NW>
 GMSB_HD unsigned leaf_pairs(const u64 *cm, int pitch, const u64 (&I)[NW], const u64 (&A)[NW]) {
     unsigned cnt = 0;
@@ -174,8 +170,13 @@ template <int NW>
 GMSB_HD u64 lane_run_task(const u64 *cm, int pitch, int need, unsigned task, int split_log2) {
     LaneState<NW> s;
     lane_begin<NW>(s, cm, pitch, task, split_log2);
-    if (need == 3) return leaf_pairs<NW>(cm, pitch, s.it, s.cur);
-    u64 total = 0, Q[NW];
+    u64 Q[NW];
+    if (need == 3) {           // the task is one pass: second member in the residue class, third anywhere in the row
+#pragma unroll
+        for (int w = 0; w < NW; ++w) Q[w] = s.cur[w] & s.stripe;
+        return leaf_pairs<NW>(cm, pitch, Q, s.cur);
+    }
+    u64 total = 0;
     while (lane_advance<NW>(s, cm, pitch, need, Q)) total += leaf_pairs<NW>(cm, pitch, Q, Q);
     return total;
 }

@@ -46,15 +46,16 @@ static u64 run_any(int nwb, const std::vector<u64> &cm, int pitch, int c, int ne
     switch (nwb) {
         case 1: return run_lanes<1>(cm, pitch, c, need, sl);
         case 2: return run_lanes<2>(cm, pitch, c, need, sl);
+        case 3: return run_lanes<3>(cm, pitch, c, need, sl);
         case 4: return run_lanes<4>(cm, pitch, c, need, sl);
+        case 5: return run_lanes<5>(cm, pitch, c, need, sl);
+        case 6: return run_lanes<6>(cm, pitch, c, need, sl);
+        case 7: return run_lanes<7>(cm, pitch, c, need, sl);
         default: return run_lanes<8>(cm, pitch, c, need, sl);
     }
 }
 
-static int bucket(int c) {
-    const int nw = (c + 63) >> 6;
-    return nw <= 1 ? 1 : nw <= 2 ? 2 : nw <= 4 ? 4 : 8;
-}
+static int bucket(int c) { return (c + 63) >> 6; }
 
 int main() {
     std::mt19937 rng(12345);
