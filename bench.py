@@ -14,9 +14,12 @@ symmetric CSR on the GPU (radix sort), keep a copy of the CSR in PINNED host mem
                gmsb_tc_total_ex (orient + schedule + count, nothing cached) + the 8-byte result back + free;
   * `roofline`: the dominant kernel (k_tc_bitmap) — its algorithmic bytes / its CUDA-event time, vs MEASURED_PEAKS;
   * `cpu_baseline` (N=1): the reference's own Par::count_total inner loop (oracle/_ref, else the oracle port) on a
-               bounded sample of the same graph, all host threads.
+               bounded sample of the same graph, all host threads;
+  * `kclique` : the other half of BASELINE.json's metric — k-clique counts/s for k = 4,5,6 on configs[2]
+               (Kronecker scale-22), sub-problems dealt over the ranks, one all-reduce (--kclique '' skips it).
 N>1 (torchrun): every rank holds the whole CSR, counts share rank/N of the schedule, one all-reduce sums the counts;
-time = max over ranks.
+time = max over ranks.  In the e2e leg rank r uploads slice r/N of the host CSR and the slices are all-gathered over
+NVLink, so h2d_bytes_per_step is still the whole CSR once (summed over ranks).
 
 Reference arm (--impl reference): rank 0 only, the reference's CPU path on bounded samples of the same workload.
 """
@@ -162,6 +165,33 @@ def run_reference(args):
     })
 
 
+def run_kclique(args, G, gd, rank, world, dev):
+    """k-clique counting (Danisch-style, degree-oriented DAG) on Kronecker scale-`kclique_scale`: the per-vertex
+    sub-problems are dealt out over the ranks (gmsb_kclique_count_ex), counts summed by one all-reduce; time = max
+    over ranks of the wall time around the C-ABI call (it returns the count, i.e. it is synchronous)."""
+    import torch
+    src, dst = G.generate_rmat(args.kclique_scale)
+    g = G.Graph.from_edgelist(src, dst, True)
+    del src, dst
+    m = g.slots // 2
+    g.kclique_count(3, rank, world)                    # builds the oriented DAG, warms the allocator
+    rows = []
+    for k in [int(x) for x in args.kclique.split(",")]:
+        gd.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        part = g.kclique_count(k, rank, world)
+        sec = gd.allreduce_max(time.perf_counter() - t0, device=dev)
+        total, = gd.allreduce_counts([part], device=dev)
+        rows.append({"k": k, "count": total, "seconds": sec, "cliques_per_s": total / sec, "edges_per_s": m / sec})
+        log(f"[rank {rank}] kclique k={k}: {total} in {sec:.3f}s")
+    out = {"workload": f"k-clique counting, Kronecker scale-{args.kclique_scale} edge factor 16 (n={g.n}, m={m}), "
+                       "degree-oriented DAG, graph replicated, per-vertex sub-problems dealt over the ranks",
+           "metric": "kclique_counts_per_sec", "unit": "cliques/s", "n_gpus": world, "results": rows}
+    g.free()
+    return out
+
+
 def run_ours(args):
     import torch
     import gms_b200 as G
@@ -246,8 +276,16 @@ def run_ours(args):
     value = m * args.steps / (ms_total * 1e-3)
 
     # ---- e2e: host CSR -> HBM -> orient -> schedule -> count -> result, nothing cached
+    # N > 1: rank r uploads slice r/N of the pinned CSR and the slices are all-gathered over NVLink (gms_b200/dist.py),
+    # so the host copy is read once instead of N times; N = 1: the plain C-ABI call on the host buffers.
+    sharded = gd.ShardedCsrUpload(off_h, nbr_h[:slots], dev) if world > 1 else None
+
     def e2e_step():
-        gg = G.Graph.from_csr(off_h.numpy(), nbr_h.numpy()[:slots])
+        if sharded is None:
+            gg = G.Graph.from_csr(off_h.numpy(), nbr_h.numpy()[:slots])
+        else:
+            off_d, nbr_d = sharded.upload()
+            gg = G.Graph.from_csr_device(n, off_d.data_ptr(), nbr_d.data_ptr())
         c, s2 = gg.tc_total_ex(reuse_plan=False, **opts)
         gg.free()
         return c, s2
@@ -331,9 +369,12 @@ def run_ours(args):
                           f"SortedSet::intersect_count over full neighbourhoods, omp dynamic"}
         except Exception as ex:      # the baseline is reported, never required
             out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(ex)}
+    g.free()
+    # ---- the other half of BASELINE.json's metric: k-clique counts/s on configs[2] (Kronecker scale-22 ef16)
+    if args.kclique:
+        out["kclique"] = run_kclique(args, G, gd, rank, world, dev)
     if rank == 0:
         emit_result(out)
-    g.free()
     gd.barrier()
     if torch.distributed.is_initialized():
         torch.distributed.destroy_process_group()
@@ -347,6 +388,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=int, default=24)
     ap.add_argument("--variant", default="auto", choices=["auto", "merge", "gallop", "bitmap"])
+    ap.add_argument("--kclique", default="4,5,6", help="clique sizes timed on configs[2] after the TC legs ('' = skip)")
+    ap.add_argument("--kclique-scale", type=int, default=22)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clocks", action="store_true")
     args = ap.parse_args()

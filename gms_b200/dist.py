@@ -3,6 +3,10 @@
 The path shards with no data-path collective: every rank builds the same graph, takes share
 `rank` of `world` of the schedule (gmsb_tc_options.part_index / part_count) and the uint64 partial counts are
 summed by a single all-reduce (NCCL over NVLink on GPUs, gloo in the CPU tests).
+
+Replicating the CSR from HOST memory is the one place a collective pays: instead of every rank pulling the whole
+2.2 GB over its own PCIe link from the same host DRAM, rank r uploads slice r of N and the slices are all-gathered
+over NVLink (`ShardedCsrUpload`), so the host is read once.
 """
 import os
 
@@ -64,3 +68,44 @@ def tc_total_sharded(graph, **opts):
     part, stats = graph.tc_total_ex(part_index=rank, part_count=world, **opts)
     total, = allreduce_counts([part])
     return total, part, stats
+
+
+def _slice_len(total, world):
+    return (total + world - 1) // world
+
+
+class ShardedCsrUpload:
+    """Replicates a host CSR (pinned int64 offsets[n+1], int32 nbrs[slots]) on every rank's device: rank r copies slice
+    r of `world` host->device, one all-gather per array fills the rest (NVLink on GPUs; gloo + CPU tensors in the CPU
+    test).  Buffers are allocated once and reused by every `upload()`; arrays are padded to a multiple of `world`."""
+
+    def __init__(self, offsets_host, nbrs_host, device):
+        self.rank, self.world = (dist.get_rank(), dist.get_world_size()) if dist.is_initialized() else (0, 1)
+        self.device = torch.device(device)
+        self.host = (offsets_host, nbrs_host)
+        self.lens = (offsets_host.numel(), nbrs_host.numel())
+        self.per = tuple(_slice_len(x, self.world) for x in self.lens)
+        self.full = tuple(torch.empty(p * self.world, dtype=h.dtype, device=self.device)
+                          for p, h in zip(self.per, self.host))
+
+    @property
+    def h2d_bytes(self):
+        """Bytes this rank copies host->device per upload."""
+        return sum(self._span(i)[1] * self.host[i].element_size() for i in range(2))
+
+    def _span(self, i):
+        lo = min(self.rank * self.per[i], self.lens[i])
+        return lo, min(self.per[i], self.lens[i] - lo)
+
+    def upload(self):
+        """Returns (offsets_dev, nbrs_dev) views of the replicated arrays (valid until the next upload)."""
+        outs = []
+        for i in range(2):
+            lo, cnt = self._span(i)
+            mine = self.full[i].narrow(0, self.rank * self.per[i], self.per[i])
+            if cnt:
+                mine.narrow(0, 0, cnt).copy_(self.host[i].narrow(0, lo, cnt), non_blocking=True)
+            if self.world > 1:
+                dist.all_gather_into_tensor(self.full[i], mine)
+            outs.append(self.full[i].narrow(0, 0, self.lens[i]))
+        return tuple(outs)

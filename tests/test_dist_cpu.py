@@ -58,3 +58,37 @@ def test_part_size_covers_everything():
     for total in (0, 1, 7, 1000):
         for parts in (1, 2, 3, 8):
             assert sum(part_size(total, i, parts) for i in range(parts)) == total
+
+
+def _upload_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    import torch
+    from gms_b200 import dist as gd
+    gd.init(backend="gloo")
+    ok = True
+    for n, slots in ((7, 23), (1, 0), (1000, 12345)):          # ragged: lengths not divisible by the world size
+        off = torch.arange(n + 1, dtype=torch.int64) * 3
+        nbr = (torch.arange(max(slots, 0), dtype=torch.int32) * 7) % 1001
+        up = gd.ShardedCsrUpload(off, nbr, "cpu")
+        for _ in range(2):                                       # buffers are reused
+            o, b = up.upload()
+            ok &= bool(torch.equal(o, off) and torch.equal(b, nbr))
+        ok &= up.h2d_bytes <= 8 * ((n + 1 + world - 1) // world) + 4 * ((slots + world - 1) // world)
+    gd.barrier()
+    q.put((rank, ok))
+
+
+def test_sharded_csr_upload_replicates_the_host_arrays():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_upload_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res)

@@ -8,7 +8,7 @@ mkdir -p gpurun_out
 python bench.py > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err
 tail -2 gpurun_out/bench_${TAG}.err
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv \
-    --log-file gpurun_out/launches_${TAG}.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-clocks \
+    --log-file gpurun_out/launches_${TAG}.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-clocks --kclique '' \
     > gpurun_out/bench_under_ncu_${TAG}.json 2> gpurun_out/bench_under_ncu_${TAG}.err
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_tc_bitmap|k_tc_merge|k_tc_gallop" -s 4 -c 4 \
     -o gpurun_out/prof_tc_${TAG} python tools/tc_sweep.py --scale 24 --reps 2 --configs '[{"variant":"auto"}]' \
