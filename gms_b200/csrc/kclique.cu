@@ -476,6 +476,7 @@ __global__ void k_class_counts(const vid_t *__restrict__ verts, int64_t cnt, con
 // above.  GMSB_KCLIQUE_IMPL=warp|lane forces one family (A/B measurements, tests); the default takes the lane
 // kernels where they are faster (measured on B200) and supported (4 <= k <= 10).
 constexpr int kLaneMinK = 5;
+constexpr int kLaneDefaultFlags = 1;
 bool use_lane_kernels(int k) {
     const char *e = std::getenv("GMSB_KCLIQUE_IMPL");
     if (e && !std::strcmp(e, "warp")) return false;
@@ -568,6 +569,9 @@ uint64_t count_on_dag(int64_t n, int64_t m, const eid_t *off, const vid_t *nbr, 
             cc.download(bound, 4);
             DevBuf<unsigned int> tickets(5);
             tickets.zero();
+            // GMSB_KCLIQUE_L3=0|1: per-warp third-level matrices (kclique_lane.cuh: warp_tasks) off / on, for A/B runs
+            const char *l3 = std::getenv("GMSB_KCLIQUE_L3");
+            const int lane_flags = l3 ? (std::atoi(l3) != 0 ? 1 : 0) : kLaneDefaultFlags;
             DevBuf<lane::u64> spill;
             // GMSB_KCLIQUE_TRACE=1: device time of every class launch on stderr (profiling aid)
             const bool trace = std::getenv("GMSB_KCLIQUE_TRACE") != nullptr;
@@ -582,15 +586,15 @@ uint64_t count_on_dag(int64_t n, int64_t m, const eid_t *off, const vid_t *nbr, 
             if (n_huge) {           // d+ > 512: CTA-wide top of the tree, compact matrices below
                 exclusive_sum(parts.p, item_base.p, n_huge + 1);
                 const int64_t n_items = item_base.get(n_huge);
-                const size_t full = lane::huge_smem_words(maxD, true) * 8;
-                const bool in_smem = full + 2048 <= r.smem_optin;
-                const size_t smem = in_smem ? full : lane::huge_smem_words(maxD, false) * 8;
                 auto launch_huge = [&](auto kern, int block) {
+                    const size_t full = lane::huge_smem_words(maxD, true, block) * 8;
+                    const bool in_smem = full + 2048 <= r.smem_optin;
+                    const size_t smem = in_smem ? full : lane::huge_smem_words(maxD, false, block) * 8;
                     GMSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                     const int grid = (int)std::min<int64_t>(n_items, (int64_t)r.sm_count);
                     if (!in_smem) spill.alloc((size_t)grid * (size_t)maxD * (size_t)lane::huge_pitch(maxD));
                     kern<<<grid, block, smem, r.stream>>>(vb.p, item_base.p, n_huge, n_items, off, nbr, k, maxD, total.p,
-                                                          tickets.p, in_smem ? nullptr : spill.p, pi, P);
+                                                          tickets.p, in_smem ? nullptr : spill.p, pi, P, lane_flags);
                     launched();
                 };
                 // 512 threads cap the kernel at 128 registers and it spills; 384 threads (168 registers, no spills) were
@@ -600,23 +604,27 @@ uint64_t count_on_dag(int64_t n, int64_t m, const eid_t *off, const vid_t *nbr, 
                 else launch_huge(lane::k_kclique_lane_huge<384>, 384);
             }
             mark();
-            auto mid = [&](auto kern, int block, int64_t first, int64_t cnt, unsigned int *ticket) {
+            // third-level boxes only where they shorten the rows: matrices of 4 or 8 words per row
+            auto mid = [&](auto kern, int block, bool boxes, int64_t first, int64_t cnt, unsigned int *ticket) {
                 if (cnt <= 0) return;
+                const int flags = boxes ? lane_flags : 0;
+                const size_t dyn = (flags & 1) ? (size_t)(block / 32) * sizeof(lane::WarpBox) : 0;
+                GMSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
                 int resident = 0;
-                GMSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, block, 0));
+                GMSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, block, dyn));
                 GMSB_REQUIRE(resident >= 1, "kclique_count: kernel does not fit on an SM");
                 const int grid = (int)std::min<int64_t>(cnt, (int64_t)r.sm_count * resident);
-                kern<<<grid, block, 0, r.stream>>>(vb.p + first, cnt, off, nbr, k, total.p, ticket, pi, P);
+                kern<<<grid, block, dyn, r.stream>>>(vb.p + first, cnt, off, nbr, k, total.p, ticket, pi, P, flags);
                 launched();
             };
-            auto mid_marked = [&](auto kern, int block, int64_t first, int64_t cnt, unsigned int *ticket) {
-                mid(kern, block, first, cnt, ticket);
+            auto mid_marked = [&](auto kern, int block, bool boxes, int64_t first, int64_t cnt, unsigned int *ticket) {
+                mid(kern, block, boxes, first, cnt, ticket);
                 mark();
             };
-            mid_marked(lane::k_kclique_lane_mid<8, 384, 2>, 384, bound[0], bound[1] - bound[0], tickets.p + 1);
-            mid_marked(lane::k_kclique_lane_mid<4, 256, 4>, 256, bound[1], bound[2] - bound[1], tickets.p + 2);
-            mid_marked(lane::k_kclique_lane_mid<2, 128, 8>, 128, bound[2], bound[3] - bound[2], tickets.p + 3);
-            mid_marked(lane::k_kclique_lane_mid<1, 128, 8>, 128, bound[3], nb - bound[3], tickets.p + 4);
+            mid_marked(lane::k_kclique_lane_mid<8, 384, 2>, 384, true, bound[0], bound[1] - bound[0], tickets.p + 1);
+            mid_marked(lane::k_kclique_lane_mid<4, 256, 4>, 256, true, bound[1], bound[2] - bound[1], tickets.p + 2);
+            mid_marked(lane::k_kclique_lane_mid<2, 128, 8>, 128, false, bound[2], bound[3] - bound[2], tickets.p + 3);
+            mid_marked(lane::k_kclique_lane_mid<1, 128, 8>, 128, false, bound[3], nb - bound[3], tickets.p + 4);
             GMSB_CUDA(cudaStreamSynchronize(r.stream));
             if (trace) {
                 static const char *names[5] = {"huge(d+>512)", "mid8(<=512)", "mid4(<=256)", "mid2(<=128)", "mid1(<=64)"};

@@ -23,11 +23,19 @@
 namespace gmsb {
 namespace lane {
 
-// count of `need`-cliques (need >= 3) in the compact graph cm[c][pitch]; tasks come from *counter (zeroed by the
-// caller, one per call); all 32 lanes of every calling warp must be here.  Returns this lane's partial count.
+__device__ __forceinline__ int split_for(int c, int block) {
+    int sl = 0;
+    while (sl < 6 && (c << sl) < 16 * block) ++sl;       // >= 16 tasks per lane keeps the tail short
+    return sl;
+}
+
+// Lanes of the calling warp(s) pull tasks [0, t_end) of the compact graph cm from *counter (zeroed by the caller) and
+// count the `need`-cliques (need >= 3) of those tasks.  Task t = (first member, residue class of the second member,
+// kclique_lane_core.cuh): the member is t >> split_log2, or alist[t >> split_log2] when a list of members is given.
+// All 32 lanes of every calling warp must be here.  Returns this lane's partial count.
 template <int NW>
-__device__ u64 lane_tasks(const u64 *cm, int pitch, int c, int need, int split_log2, unsigned *counter, int lane) {
-    const unsigned ntasks = (unsigned)c << split_log2;
+__device__ __forceinline__ u64 lane_tasks(const u64 *cm, int pitch, unsigned t_end, int need, int split_log2,
+                                          unsigned *counter, int lane, const unsigned short *alist) {
     u64 total = 0;
     LaneState<NW> s;
     s.level = -1;
@@ -42,8 +50,12 @@ __device__ u64 lane_tasks(const u64 *cm, int pitch, int c, int need, int split_l
             base = __shfl_sync(0xffffffffu, base, leader);
             if (want) {
                 const unsigned t = base + (unsigned)__popc(idle & ((1u << lane) - 1u));
-                if (t >= ntasks) exhausted = true;
-                else lane_begin<NW>(s, cm, pitch, t, split_log2);
+                if (t >= t_end) exhausted = true;
+                else {
+                    const unsigned m = t >> split_log2;
+                    lane_begin<NW>(s, cm, pitch, alist ? (int)alist[m] : (int)m, (int)(t & ((1u << split_log2) - 1u)),
+                                   split_log2);
+                }
             }
         }
         if (__all_sync(0xffffffffu, s.level < 0)) break;
@@ -62,10 +74,93 @@ __device__ u64 lane_tasks(const u64 *cm, int pitch, int c, int need, int split_l
     return total;
 }
 
-__device__ __forceinline__ int split_for(int c, int block) {
-    int sl = 0;
-    while (sl < 6 && (c << sl) < 16 * block) ++sl;       // >= 16 tasks per lane keeps the tail short
-    return sl;
+// ---- third level: per-warp compact matrix ------------------------------------------------------------------------------
+// With four or more vertices still to pick below a member a of cm, the search below a runs in a matrix of its own:
+// the WARP re-indexes row a (<= 128 members) into M3 (rows of 1-2 words instead of up to 8) and its lanes pull M3's
+// tasks from a warp-local ticket.  Deep in the tree the sets hold 3-5 members per word of the parent's index space, so
+// every AND + popcount there is mostly zeros; one more re-indexing halves to quarters the words per step and fills
+// them.  Rows that are too large for M3 are put on a list and searched in cm afterwards by all lanes of the CTA.
+constexpr int kC3Max = 128;
+constexpr int kP3 = 3;                       // pitch of M3 (2 valid words, odd)
+struct WarpBox {
+    u64 m3[kC3Max * kP3];
+    u64 set[8];
+    int prefix[8];
+    unsigned short list[kC3Max];
+    unsigned counter;
+    unsigned pad;
+};
+struct CtaBigRows {                          // members of cm whose row does not fit M3
+    unsigned short list[kCMax];
+    unsigned count;
+    unsigned counter;                        // ticket of the lane tasks over these rows
+};
+
+// nw = valid 64-bit words per row of cm (<= 8); every warp of the CTA calls this with the same arguments
+__device__ u64 warp_tasks(const u64 *cm, int pitch, int nw, int c, int need, unsigned *counter, WarpBox *box,
+                          CtaBigRows *big, int lane) {
+    u64 total = 0;
+    for (;;) {
+        unsigned a = 0;
+        if (lane == 0) a = atomicAdd(counter, 1u);
+        a = __shfl_sync(0xffffffffu, a, 0);
+        if (a >= (unsigned)c) break;
+        const u64 *row = cm + (size_t)a * pitch;
+        const u64 mine = lane < nw ? row[lane] : 0ull;
+        const int pc = __popcll(mine);
+        int incl = pc;
+        for (int o = 1; o < 8; o <<= 1) {
+            const int x = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += x;
+        }
+        const int c3 = __shfl_sync(0xffffffffu, incl, 7);         // lanes >= nw add 0
+        if (c3 < need - 1) continue;
+        if (c3 > kC3Max) {
+            if (lane == 0) big->list[atomicAdd(&big->count, 1u)] = (unsigned short)a;
+            continue;
+        }
+        __syncwarp();
+        if (lane == 0) box->counter = 0u;
+        if (lane < 8) { box->set[lane] = mine; box->prefix[lane] = incl - pc; }
+        __syncwarp();
+        for (int p = lane; p < nw * 64; p += 32)
+            if ((box->set[p >> 6] >> (p & 63)) & 1ull)
+                box->list[compact_index(box->set, box->prefix, p)] = (unsigned short)p;
+        __syncwarp();
+        const int nw3 = c3 <= 64 ? 1 : 2;
+        for (int m = lane; m < c3; m += 32) {
+            const int pa = box->list[m];
+            compact_row(box->set, box->prefix, nw, cm + (size_t)pa * pitch, pa, box->m3 + (size_t)m * kP3, nw3);
+        }
+        __syncwarp();
+        const int sl = split_for(c3, 32);
+        total += nw3 == 1 ? lane_tasks<1>(box->m3, kP3, (unsigned)c3 << sl, need - 1, sl, &box->counter, lane, nullptr)
+                          : lane_tasks<2>(box->m3, kP3, (unsigned)c3 << sl, need - 1, sl, &box->counter, lane, nullptr);
+        __syncwarp();
+    }
+    return total;
+}
+
+// `need`-cliques (need >= 3) of the compact graph cm[c][pitch] (NW valid words per row) by ALL threads of the CTA;
+// *counter and *big are zeroed by the caller (and a barrier passed).  Per-lane tasks over every member, or — when the
+// search below a member is deep enough to pay for another re-indexing — per-warp third-level matrices first and
+// per-lane tasks over the rows that did not fit one.
+template <int NW>
+__device__ __forceinline__ u64 count_compact(const u64 *cm, int pitch, int c, int need, int block, unsigned *counter,
+                                             WarpBox *box, CtaBigRows *big, int lane) {
+    u64 total = 0;
+    unsigned t_end = (unsigned)c;
+    int sl = split_for(c, block);
+    const unsigned short *alist = nullptr;
+    if (need >= 5 && box) {
+        total = warp_tasks(cm, pitch, NW, c, need, counter, box, big, lane);
+        __syncthreads();
+        t_end = big->count;
+        sl = 6;
+        alist = big->list;
+        counter = &big->counter;
+    }
+    return total + lane_tasks<NW>(cm, pitch, t_end << sl, need, sl, counter, lane, alist);
 }
 
 // rows of the bit matrix of S (|S| = D): warp per member i streams N+(S[i]) and looks every element up in S
@@ -95,18 +190,21 @@ template <int NWB, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB)
 k_kclique_lane_mid(const vid_t *__restrict__ verts, int64_t count, const eid_t *__restrict__ off,
                    const vid_t *__restrict__ nbr, int k, unsigned long long *__restrict__ total,
-                   unsigned int *__restrict__ ticket, int pi, int P) {
+                   unsigned int *__restrict__ ticket, int pi, int P, int flags) {
     constexpr int DMAX = 64 * NWB;
     constexpr int PITCH = pitch_for(NWB);
     __shared__ vid_t S[DMAX];
     __shared__ u64 M[DMAX * PITCH];
     __shared__ unsigned long long red[BLOCK / 32];
     __shared__ unsigned int s_item, s_counter;
+    __shared__ CtaBigRows s_big;
+    extern __shared__ u64 dyn64[];                  // one WarpBox per warp when the third level is enabled (flags & 1)
     const int tid = threadIdx.x, lane = tid & 31;
+    WarpBox *box = (flags & 1) ? reinterpret_cast<WarpBox *>(dyn64) + (tid >> 5) : nullptr;
     u64 acc = 0;
     for (;;) {
         __syncthreads();
-        if (tid == 0) { s_item = atomicAdd(ticket, 1u); s_counter = 0; }
+        if (tid == 0) { s_item = atomicAdd(ticket, 1u); s_counter = 0; s_big.count = 0; s_big.counter = 0; }
         __syncthreads();
         const int64_t t = pi + (int64_t)s_item * P;
         if (t >= count) break;
@@ -119,7 +217,7 @@ k_kclique_lane_mid(const vid_t *__restrict__ verts, int64_t count, const eid_t *
         build_rows<BLOCK>(S, D, M, PITCH, off, nbr, tid);
         __syncthreads();
         // u is the first clique vertex; k-1 more inside the matrix
-        acc += lane_tasks<NWB>(M, PITCH, D, k - 1, split_for(D, BLOCK), &s_counter, lane);
+        acc += count_compact<NWB>(M, PITCH, D, k - 1, BLOCK, &s_counter, box, &s_big, lane);
     }
     const unsigned long long s = block_sum(acc, red);
     if (tid == 0 && s) atomicAdd(total, s);
@@ -130,10 +228,11 @@ constexpr int kStackLevels = 16;
 
 __host__ __device__ inline int huge_pitch(int maxD) { return ((maxD + 63) >> 6) | 1; }
 // dynamic shared memory of k_kclique_lane_huge in 64-bit words (matrix included unless it is spilled to global)
-__host__ __device__ inline size_t huge_smem_words(int maxD, bool matrix_in_smem) {
+__host__ __device__ inline size_t huge_smem_words(int maxD, bool matrix_in_smem, int block) {
     const size_t P1 = (size_t)huge_pitch(maxD);
     return (matrix_in_smem ? (size_t)maxD * P1 : 0) + (size_t)kCMax * pitch_for(8) + (size_t)kStackLevels * P1 +
-           (size_t)((maxD + 1) >> 1) + ((P1 + 2) >> 1) + (size_t)(kCMax / 4);
+           (size_t)((maxD + 1) >> 1) + ((P1 + 2) >> 1) + (size_t)(kCMax / 4) +
+           (size_t)(block / 32) * (sizeof(WarpBox) / 8);
 }
 
 template <int BLOCK>
@@ -141,7 +240,7 @@ __global__ void __launch_bounds__(BLOCK, 1)
 k_kclique_lane_huge(const vid_t *__restrict__ verts, const int64_t *__restrict__ item_base, int64_t nverts,
                     int64_t count, const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, int k, int maxD,
                     unsigned long long *__restrict__ total, unsigned int *__restrict__ ticket,
-                    u64 *__restrict__ spill, int pi, int P) {
+                    u64 *__restrict__ spill, int pi, int P, int flags) {
     extern __shared__ u64 smem64[];
     const int P1 = huge_pitch(maxD);
     u64 *M1 = spill ? spill + (size_t)blockIdx.x * ((size_t)maxD * P1) : smem64;
@@ -150,11 +249,14 @@ k_kclique_lane_huge(const vid_t *__restrict__ verts, const int64_t *__restrict__
     u64 *stack = sp;               sp += (size_t)kStackLevels * P1;
     vid_t *S = reinterpret_cast<vid_t *>(sp);            sp += (maxD + 1) >> 1;
     int *prefix = reinterpret_cast<int *>(sp);           sp += (P1 + 2) >> 1;
-    unsigned short *list = reinterpret_cast<unsigned short *>(sp);
+    unsigned short *list = reinterpret_cast<unsigned short *>(sp);         sp += kCMax / 4;
+    WarpBox *boxes = reinterpret_cast<WarpBox *>(sp);
     __shared__ unsigned long long red[BLOCK / 32];
     __shared__ unsigned int s_item, s_counter;
+    __shared__ CtaBigRows s_big;
     __shared__ int s_c;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    WarpBox *box = (flags & 1) ? boxes + warp : nullptr;
     u64 acc = 0;
     for (;;) {
         __syncthreads();
@@ -229,7 +331,7 @@ k_kclique_lane_huge(const vid_t *__restrict__ verts, const int64_t *__restrict__
                                     carry += __shfl_sync(0xffffffffu, incl, 31);
                                 }
                             }
-                            if (tid == 0) s_counter = 0;
+                            if (tid == 0) { s_counter = 0; s_big.count = 0; s_big.counter = 0; }
                             __syncthreads();
                             for (int p = tid; p < D; p += BLOCK)
                                 if ((set[p >> 6] >> (p & 63)) & 1ull)
@@ -242,16 +344,15 @@ k_kclique_lane_huge(const vid_t *__restrict__ verts, const int64_t *__restrict__
                                 compact_row(set, prefix, W1, M1 + (size_t)pa * P1, pa, M2 + (size_t)a * pitch2, nwb);
                             }
                             __syncthreads();
-                            const int sl = split_for(c, BLOCK);
                             switch (nwb) {
-                                case 1: acc += lane_tasks<1>(M2, pitch2, c, need, sl, &s_counter, lane); break;
-                                case 2: acc += lane_tasks<2>(M2, pitch2, c, need, sl, &s_counter, lane); break;
-                                case 3: acc += lane_tasks<3>(M2, pitch2, c, need, sl, &s_counter, lane); break;
-                                case 4: acc += lane_tasks<4>(M2, pitch2, c, need, sl, &s_counter, lane); break;
-                                case 5: acc += lane_tasks<5>(M2, pitch2, c, need, sl, &s_counter, lane); break;
-                                case 6: acc += lane_tasks<6>(M2, pitch2, c, need, sl, &s_counter, lane); break;
-                                case 7: acc += lane_tasks<7>(M2, pitch2, c, need, sl, &s_counter, lane); break;
-                                default: acc += lane_tasks<8>(M2, pitch2, c, need, sl, &s_counter, lane); break;
+                                case 1: acc += count_compact<1>(M2, pitch2, c, need, BLOCK, &s_counter, box, &s_big, lane); break;
+                                case 2: acc += count_compact<2>(M2, pitch2, c, need, BLOCK, &s_counter, box, &s_big, lane); break;
+                                case 3: acc += count_compact<3>(M2, pitch2, c, need, BLOCK, &s_counter, box, &s_big, lane); break;
+                                case 4: acc += count_compact<4>(M2, pitch2, c, need, BLOCK, &s_counter, box, &s_big, lane); break;
+                                case 5: acc += count_compact<5>(M2, pitch2, c, need, BLOCK, &s_counter, box, &s_big, lane); break;
+                                case 6: acc += count_compact<6>(M2, pitch2, c, need, BLOCK, &s_counter, box, &s_big, lane); break;
+                                case 7: acc += count_compact<7>(M2, pitch2, c, need, BLOCK, &s_counter, box, &s_big, lane); break;
+                                default: acc += count_compact<8>(M2, pitch2, c, need, BLOCK, &s_counter, box, &s_big, lane); break;
                             }
                         } else {
                             expand = true;

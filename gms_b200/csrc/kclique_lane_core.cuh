@@ -80,11 +80,10 @@ struct LaneState {
     int level;        // -1 = idle
 };
 
-// task = (first member a, residue class of the second member)
+// task = (first member a, residue class `cls` of the second member)
 template <int NW>
-GMSB_HD void lane_begin(LaneState<NW> &s, const u64 *cm, int pitch, unsigned task, int split_log2) {
-    const int a = (int)(task >> split_log2);
-    s.stripe = stripe_mask(split_log2, (int)(task & ((1u << split_log2) - 1u)));
+GMSB_HD void lane_begin(LaneState<NW> &s, const u64 *cm, int pitch, int a, int cls, int split_log2) {
+    s.stripe = stripe_mask(split_log2, cls);
     const u64 *row = cm + (size_t)a * pitch;
 #pragma unroll
     for (int w = 0; w < NW; ++w) s.cur[w] = row[w];
@@ -147,7 +146,9 @@ GMSB_HD bool lane_advance(LaneState<NW> &s, const u64 *cm, int pitch, int need, 
 // sum over x in I of |A ∩ row(x)|: the last two clique vertices in one pass (row(x) only has members after x, so
 // the words below x's own are skipped).  A variant that added the rows of seven members as bit planes (carry-save
 // adders, 3 popcounts per word instead of 7) was measured on B200 and was SLOWER (scale-22 k=6: 44 s vs 38 s): the
-// candidate sets this deep hold only 3-5 members per 64-bit word, so the groups were mostly padding.
+// candidate sets this deep hold only 3-5 members per 64-bit word, so the groups were mostly padding.  So was a
+// single loop over all members with the words below x's own predicated off (68 s vs 36 s): a predicated-off POPC
+// still takes its slot on the quarter-rate pipe.
 template <int NW>
 GMSB_HD unsigned leaf_pairs(const u64 *cm, int pitch, const u64 (&I)[NW], const u64 (&A)[NW]) {
     unsigned cnt = 0;
@@ -169,7 +170,7 @@ GMSB_HD unsigned leaf_pairs(const u64 *cm, int pitch, const u64 (&I)[NW], const 
 template <int NW>
 GMSB_HD u64 lane_run_task(const u64 *cm, int pitch, int need, unsigned task, int split_log2) {
     LaneState<NW> s;
-    lane_begin<NW>(s, cm, pitch, task, split_log2);
+    lane_begin<NW>(s, cm, pitch, (int)(task >> split_log2), (int)(task & ((1u << split_log2) - 1u)), split_log2);
     u64 Q[NW];
     if (need == 3) {           // the task is one pass: second member in the residue class, third anywhere in the row
 #pragma unroll

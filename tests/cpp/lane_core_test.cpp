@@ -57,6 +57,19 @@ static u64 run_any(int nwb, const std::vector<u64> &cm, int pitch, int c, int ne
 
 static int bucket(int c) { return (c + 63) >> 6; }
 
+static u64 run_task_any(int nw, const std::vector<u64> &cm, int pitch, int need, unsigned task, int sl) {
+    switch (nw) {
+        case 1: return lane_run_task<1>(cm.data(), pitch, need, task, sl);
+        case 2: return lane_run_task<2>(cm.data(), pitch, need, task, sl);
+        case 3: return lane_run_task<3>(cm.data(), pitch, need, task, sl);
+        case 4: return lane_run_task<4>(cm.data(), pitch, need, task, sl);
+        case 5: return lane_run_task<5>(cm.data(), pitch, need, task, sl);
+        case 6: return lane_run_task<6>(cm.data(), pitch, need, task, sl);
+        case 7: return lane_run_task<7>(cm.data(), pitch, need, task, sl);
+        default: return lane_run_task<8>(cm.data(), pitch, need, task, sl);
+    }
+}
+
 int main() {
     std::mt19937 rng(12345);
     int fails = 0, checks = 0;
@@ -140,6 +153,48 @@ int main() {
                 ++checks;
                 if (got != want) { ++fails; std::printf("FAIL compact-count D=%d c=%d need=%d got=%llu want=%llu\n", D, c, need, got, want); }
             }
+        }
+    }
+    // 3. third level (kclique_lane.cuh: warp_tasks): below a member a whose row has <= 128 members the search runs in
+    //    a re-indexed matrix M3 (pitch 3) with need-1; larger rows are searched in cm as 64 residue-class tasks
+    for (int c : {90, 200, 220, 400, 512}) {
+        auto adj = c == 220 ? random_dag(c, 0.8, rng, false)          // rows of up to ~175 members: too large for M3
+                            : random_dag(c, c <= 200 ? 0.6 : 0.3, rng, true);
+        const int nw = bucket(c), pitch = pitch_for(nw);
+        std::vector<u64> cm((size_t)c * pitch, 0);
+        for (int a = 0; a < c; ++a)
+            for (int b = a + 1; b < c; ++b)
+                if (adj[a][b]) cm[(size_t)a * pitch + (b >> 6)] |= 1ull << (b & 63);
+        std::vector<int> all(c);
+        for (int i = 0; i < c; ++i) all[i] = i;
+        for (int need : {5, 6}) {
+            if (c > 200 && need > 5) continue;
+            const u64 want = brute(adj, all, need);
+            u64 got = 0;
+            int compacted = 0, big = 0;
+            for (int a = 0; a < c; ++a) {
+                const u64 *row = cm.data() + (size_t)a * pitch;
+                int prefix[8] = {0}, c3 = 0;
+                for (int w = 0; w < nw; ++w) { prefix[w] = c3; c3 += popc64(row[w]); }
+                if (c3 < need - 1) continue;
+                if (c3 > 128) {
+                    ++big;
+                    for (unsigned st = 0; st < 64; ++st) got += run_task_any(nw, cm, pitch, need, ((unsigned)a << 6) | st, 6);
+                    continue;
+                }
+                ++compacted;
+                std::vector<int> list(c3);
+                for (int p = 0; p < nw * 64; ++p)
+                    if ((row[p >> 6] >> (p & 63)) & 1) list[compact_index(row, prefix, p)] = p;
+                const int nw3 = c3 <= 64 ? 1 : 2;
+                std::vector<u64> m3((size_t)c3 * 3, ~0ull);
+                for (int m = 0; m < c3; ++m)
+                    compact_row(row, prefix, nw, cm.data() + (size_t)list[m] * pitch, list[m], m3.data() + (size_t)m * 3, nw3);
+                got += run_any(nw3, m3, 3, c3, need - 1, 3);
+            }
+            ++checks;
+            if (got != want) { ++fails; std::printf("FAIL third-level c=%d need=%d got=%llu want=%llu\n", c, need, got, want); }
+            std::printf("third level c=%d need=%d: %d rows re-indexed, %d searched in place\n", c, need, compacted, big);
         }
     }
     std::printf("%d checks, %d failures\n", checks, fails);
