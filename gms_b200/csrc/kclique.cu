@@ -587,14 +587,14 @@ uint64_t count_on_dag(int64_t n, int64_t m, const eid_t *off, const vid_t *nbr, 
                 exclusive_sum(parts.p, item_base.p, n_huge + 1);
                 const int64_t n_items = item_base.get(n_huge);
                 auto launch_huge = [&](auto kern, int block) {
-                    const size_t full = lane::huge_smem_words(maxD, true, block) * 8;
+                    const size_t full = lane::huge_smem_words(maxD, true) * 8;
                     const bool in_smem = full + 2048 <= r.smem_optin;
-                    const size_t smem = in_smem ? full : lane::huge_smem_words(maxD, false, block) * 8;
+                    const size_t smem = in_smem ? full : lane::huge_smem_words(maxD, false) * 8;
                     GMSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                     const int grid = (int)std::min<int64_t>(n_items, (int64_t)r.sm_count);
                     if (!in_smem) spill.alloc((size_t)grid * (size_t)maxD * (size_t)lane::huge_pitch(maxD));
                     kern<<<grid, block, smem, r.stream>>>(vb.p, item_base.p, n_huge, n_items, off, nbr, k, maxD, total.p,
-                                                          tickets.p, in_smem ? nullptr : spill.p, pi, P, lane_flags);
+                                                          tickets.p, in_smem ? nullptr : spill.p, pi, P);
                     launched();
                 };
                 // 512 threads cap the kernel at 128 registers and it spills; 384 threads (168 registers, no spills) were

@@ -12,7 +12,9 @@
 //     third vertex) are dealt to the lanes of the CTA through a shared ticket;
 //   * d+(u) > 512 : the CTA walks the top of the tree together (one AND per level, a handful of barriers) until the
 //     candidate set has <= 512 members, re-indexes that set into a second, compact matrix (<= 8 words per row) and
-//     deals its tasks to the lanes; with two vertices left the pairs are counted straight off the big matrix.
+//     deals its tasks to the lanes; with two vertices left the pairs are counted straight off the big matrix;
+//   * 129 <= d+(u) <= 512 and four or more vertices left below the second one: a warp re-indexes the second
+//     vertex's row once more into its own small matrix (warp_tasks).
 // A lane keeps its candidate sets in registers (kclique_lane_core.cuh); only the path is remembered per level, the
 // parent's set is recomputed on the way back, so there is no per-lane stack memory at all.
 #pragma once
@@ -80,6 +82,10 @@ __device__ __forceinline__ u64 lane_tasks(const u64 *cm, int pitch, unsigned t_e
 // tasks from a warp-local ticket.  Deep in the tree the sets hold 3-5 members per word of the parent's index space, so
 // every AND + popcount there is mostly zeros; one more re-indexing halves to quarters the words per step and fills
 // them.  Rows that are too large for M3 are put on a list and searched in cm afterwards by all lanes of the CTA.
+// Used by the 129..512 classes (measured at scale 22: k = 6 mid8 4.53 -> 3.56 s; k = 7 mid8 -18 %, mid4 -19 %).  In the
+// d+ > 512 kernel it was NOT a win (k = 7: +18 %): rows of M2 mostly exceed 128 members, a warp's 32 lanes drain at
+// the end of every member, and the extra live state pushed that kernel into register spills — it deals every task of
+// M2 to the lanes of the whole CTA instead.
 constexpr int kC3Max = 128;
 constexpr int kP3 = 3;                       // pitch of M3 (2 valid words, odd)
 struct WarpBox {
@@ -228,11 +234,10 @@ constexpr int kStackLevels = 16;
 
 __host__ __device__ inline int huge_pitch(int maxD) { return ((maxD + 63) >> 6) | 1; }
 // dynamic shared memory of k_kclique_lane_huge in 64-bit words (matrix included unless it is spilled to global)
-__host__ __device__ inline size_t huge_smem_words(int maxD, bool matrix_in_smem, int block) {
+__host__ __device__ inline size_t huge_smem_words(int maxD, bool matrix_in_smem) {
     const size_t P1 = (size_t)huge_pitch(maxD);
     return (matrix_in_smem ? (size_t)maxD * P1 : 0) + (size_t)kCMax * pitch_for(8) + (size_t)kStackLevels * P1 +
-           (size_t)((maxD + 1) >> 1) + ((P1 + 2) >> 1) + (size_t)(kCMax / 4) +
-           (size_t)(block / 32) * (sizeof(WarpBox) / 8);
+           (size_t)((maxD + 1) >> 1) + ((P1 + 2) >> 1) + (size_t)(kCMax / 4);
 }
 
 template <int BLOCK>
@@ -240,7 +245,7 @@ __global__ void __launch_bounds__(BLOCK, 1)
 k_kclique_lane_huge(const vid_t *__restrict__ verts, const int64_t *__restrict__ item_base, int64_t nverts,
                     int64_t count, const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, int k, int maxD,
                     unsigned long long *__restrict__ total, unsigned int *__restrict__ ticket,
-                    u64 *__restrict__ spill, int pi, int P, int flags) {
+                    u64 *__restrict__ spill, int pi, int P) {
     extern __shared__ u64 smem64[];
     const int P1 = huge_pitch(maxD);
     u64 *M1 = spill ? spill + (size_t)blockIdx.x * ((size_t)maxD * P1) : smem64;
@@ -249,14 +254,11 @@ k_kclique_lane_huge(const vid_t *__restrict__ verts, const int64_t *__restrict__
     u64 *stack = sp;               sp += (size_t)kStackLevels * P1;
     vid_t *S = reinterpret_cast<vid_t *>(sp);            sp += (maxD + 1) >> 1;
     int *prefix = reinterpret_cast<int *>(sp);           sp += (P1 + 2) >> 1;
-    unsigned short *list = reinterpret_cast<unsigned short *>(sp);         sp += kCMax / 4;
-    WarpBox *boxes = reinterpret_cast<WarpBox *>(sp);
+    unsigned short *list = reinterpret_cast<unsigned short *>(sp);
     __shared__ unsigned long long red[BLOCK / 32];
     __shared__ unsigned int s_item, s_counter;
-    __shared__ CtaBigRows s_big;
     __shared__ int s_c;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    WarpBox *box = (flags & 1) ? boxes + warp : nullptr;
     u64 acc = 0;
     for (;;) {
         __syncthreads();
@@ -331,7 +333,7 @@ k_kclique_lane_huge(const vid_t *__restrict__ verts, const int64_t *__restrict__
                                     carry += __shfl_sync(0xffffffffu, incl, 31);
                                 }
                             }
-                            if (tid == 0) { s_counter = 0; s_big.count = 0; s_big.counter = 0; }
+                            if (tid == 0) s_counter = 0;
                             __syncthreads();
                             for (int p = tid; p < D; p += BLOCK)
                                 if ((set[p >> 6] >> (p & 63)) & 1ull)
@@ -344,15 +346,16 @@ k_kclique_lane_huge(const vid_t *__restrict__ verts, const int64_t *__restrict__
                                 compact_row(set, prefix, W1, M1 + (size_t)pa * P1, pa, M2 + (size_t)a * pitch2, nwb);
                             }
                             __syncthreads();
+                            const int sl = split_for(c, BLOCK);
                             switch (nwb) {
-                                case 1: acc += count_compact<1>(M2, pitch2, c, need, BLOCK, &s_counter, box, &s_big, lane); break;
-                                case 2: acc += count_compact<2>(M2, pitch2, c, need, BLOCK, &s_counter, box, &s_big, lane); break;
-                                case 3: acc += count_compact<3>(M2, pitch2, c, need, BLOCK, &s_counter, box, &s_big, lane); break;
-                                case 4: acc += count_compact<4>(M2, pitch2, c, need, BLOCK, &s_counter, box, &s_big, lane); break;
-                                case 5: acc += count_compact<5>(M2, pitch2, c, need, BLOCK, &s_counter, box, &s_big, lane); break;
-                                case 6: acc += count_compact<6>(M2, pitch2, c, need, BLOCK, &s_counter, box, &s_big, lane); break;
-                                case 7: acc += count_compact<7>(M2, pitch2, c, need, BLOCK, &s_counter, box, &s_big, lane); break;
-                                default: acc += count_compact<8>(M2, pitch2, c, need, BLOCK, &s_counter, box, &s_big, lane); break;
+                                case 1: acc += lane_tasks<1>(M2, pitch2, (unsigned)c << sl, need, sl, &s_counter, lane, nullptr); break;
+                                case 2: acc += lane_tasks<2>(M2, pitch2, (unsigned)c << sl, need, sl, &s_counter, lane, nullptr); break;
+                                case 3: acc += lane_tasks<3>(M2, pitch2, (unsigned)c << sl, need, sl, &s_counter, lane, nullptr); break;
+                                case 4: acc += lane_tasks<4>(M2, pitch2, (unsigned)c << sl, need, sl, &s_counter, lane, nullptr); break;
+                                case 5: acc += lane_tasks<5>(M2, pitch2, (unsigned)c << sl, need, sl, &s_counter, lane, nullptr); break;
+                                case 6: acc += lane_tasks<6>(M2, pitch2, (unsigned)c << sl, need, sl, &s_counter, lane, nullptr); break;
+                                case 7: acc += lane_tasks<7>(M2, pitch2, (unsigned)c << sl, need, sl, &s_counter, lane, nullptr); break;
+                                default: acc += lane_tasks<8>(M2, pitch2, (unsigned)c << sl, need, sl, &s_counter, lane, nullptr); break;
                             }
                         } else {
                             expand = true;
