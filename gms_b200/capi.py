@@ -79,6 +79,9 @@ SIGNATURES = {
     "gmsb_tc_vertex2": (C.c_int, [C.c_void_p, _i64p]),
     "gmsb_intersect_count_batch": (C.c_int, [C.c_void_p, C.c_int64, _i32p, _i32p, _u64p]),
     "gmsb_intersect_batch": (C.c_int, [C.c_void_p, C.c_int64, _i32p, _i32p, _i64p, C.c_void_p, C.c_int64]),
+    "gmsb_difference_batch": (C.c_int, [C.c_void_p, C.c_int64, _i32p, _i32p, _i64p, C.c_void_p, C.c_int64]),
+    "gmsb_union_batch": (C.c_int, [C.c_void_p, C.c_int64, _i32p, _i32p, _i64p, C.c_void_p, C.c_int64]),
+    "gmsb_union_count_batch": (C.c_int, [C.c_void_p, C.c_int64, _i32p, _i32p, _u64p]),
     "gmsb_pair_similarity": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, _i32p, _i32p, _f64p]),
     "gmsb_edge_similarity": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int64)]),
     "gmsb_kclique_count": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]),
@@ -283,13 +286,29 @@ class Graph:
         _check(lib().gmsb_intersect_count_batch(self.h, len(a), _ids(a), _ids(b), out))
         return out[:len(a)]
 
-    def intersect_batch(self, a, b):
+    def _two_pass(self, fn, a, b):
         assert len(a) == len(b)
         off = np.zeros(len(a) + 1, np.int64)
-        _check(lib().gmsb_intersect_batch(self.h, len(a), _ids(a), _ids(b), off, None, 0))
+        _check(fn(self.h, len(a), _ids(a), _ids(b), off, None, 0))
         elems = np.zeros(max(int(off[-1]), 1), np.int32)
-        _check(lib().gmsb_intersect_batch(self.h, len(a), _ids(a), _ids(b), off, elems.ctypes.data, len(elems)))
+        _check(fn(self.h, len(a), _ids(a), _ids(b), off, elems.ctypes.data, len(elems)))
         return off, elems[:off[-1]]
+
+    def intersect_batch(self, a, b):
+        return self._two_pass(lib().gmsb_intersect_batch, a, b)
+
+    def difference_batch(self, a, b):
+        """N(a[i]) \\ N(b[i]) for every pair: (offsets, elements), ascending inside each result."""
+        return self._two_pass(lib().gmsb_difference_batch, a, b)
+
+    def union_batch(self, a, b):
+        return self._two_pass(lib().gmsb_union_batch, a, b)
+
+    def union_count_batch(self, a, b):
+        assert len(a) == len(b)
+        out = np.zeros(max(len(a), 1), np.uint64)
+        _check(lib().gmsb_union_count_batch(self.h, len(a), _ids(a), _ids(b), out))
+        return out[:len(a)]
 
     def pair_similarity(self, metric, a, b):
         assert len(a) == len(b)

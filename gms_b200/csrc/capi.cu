@@ -325,6 +325,26 @@ GMSB_API int gmsb_intersect_batch(gmsb_graph_t g, int64_t np, const int32_t *a, 
         intersect_batch(G(g), np, a, b, out_offsets, out_elems, cap);
     });
 }
+GMSB_API int gmsb_difference_batch(gmsb_graph_t g, int64_t np, const int32_t *a, const int32_t *b, int64_t *out_offsets,
+                                   int32_t *out_elems, int64_t cap) {
+    return guarded([&] {
+        GMSB_REQUIRE(np >= 0 && out_offsets && (np == 0 || (a && b)), "difference_batch: bad arguments");
+        difference_batch(G(g), np, a, b, out_offsets, out_elems, cap);
+    });
+}
+GMSB_API int gmsb_union_batch(gmsb_graph_t g, int64_t np, const int32_t *a, const int32_t *b, int64_t *out_offsets,
+                              int32_t *out_elems, int64_t cap) {
+    return guarded([&] {
+        GMSB_REQUIRE(np >= 0 && out_offsets && (np == 0 || (a && b)), "union_batch: bad arguments");
+        union_batch(G(g), np, a, b, out_offsets, out_elems, cap);
+    });
+}
+GMSB_API int gmsb_union_count_batch(gmsb_graph_t g, int64_t np, const int32_t *a, const int32_t *b, uint64_t *out) {
+    return guarded([&] {
+        GMSB_REQUIRE(np >= 0 && (np == 0 || (a && b && out)), "union_count_batch: bad arguments");
+        union_count_batch(G(g), np, a, b, out);
+    });
+}
 GMSB_API int gmsb_pair_similarity(gmsb_graph_t g, int metric, int64_t np, const int32_t *a, const int32_t *b, double *out) {
     return guarded([&] {
         GMSB_REQUIRE(np >= 0 && (np == 0 || (a && b && out)), "pair_similarity: bad arguments");

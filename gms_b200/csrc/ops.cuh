@@ -12,6 +12,11 @@ void generate_uniform(int scale, int64_t m, vid_t *src, vid_t *dst);
 void intersect_count_batch(Graph &g, int64_t np, const vid_t *a, const vid_t *b, uint64_t *out);
 void intersect_batch(Graph &g, int64_t np, const vid_t *a, const vid_t *b, int64_t *out_offsets, vid_t *out_elems,
                      int64_t cap);
+void difference_batch(Graph &g, int64_t np, const vid_t *a, const vid_t *b, int64_t *out_offsets, vid_t *out_elems,
+                      int64_t cap);
+void union_batch(Graph &g, int64_t np, const vid_t *a, const vid_t *b, int64_t *out_offsets, vid_t *out_elems,
+                 int64_t cap);
+void union_count_batch(Graph &g, int64_t np, const vid_t *a, const vid_t *b, uint64_t *out);
 void pair_similarity(Graph &g, int metric, int64_t np, const vid_t *a, const vid_t *b, double *out);
 void edge_similarity(Graph &g, int metric, double *out, int64_t *m_out);
 

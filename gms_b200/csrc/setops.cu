@@ -2,6 +2,7 @@
 //
 // Replaces:
 //   SortedSetBase::intersect_count / intersect      gms/representations/sets/sorted_set.h:160-182
+//   SortedSetBase::union_with / union_count / difference   sorted_set.h:104-109,140,184-189
 //   GMS::VertexSim::vertex_similarity<Metric>       gms/algorithms/set_based/vertex_similarity/vertex_similarity.h:30-221
 //
 // One warp per vertex pair; merge path for balanced pairs, galloping for skewed ones (isect.cuh).  The similarity
@@ -30,7 +31,7 @@ __device__ __forceinline__ uint32_t pair_count(const vid_t *a, int na, const vid
 __global__ void __launch_bounds__(kWarps * 32)
 k_pair_count(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, int64_t n, int64_t np,
              const vid_t *__restrict__ pa, const vid_t *__restrict__ pb, unsigned long long *__restrict__ out,
-             int *__restrict__ bad) {
+             int *__restrict__ bad, int union_mode) {
     __shared__ vid_t stage[kWarps][kMergeTile + 2];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -42,7 +43,8 @@ k_pair_count(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, int64
         unsigned long long c = pair_count(nbr + oa, (int)(off[a + 1] - oa), nbr + ob, (int)(off[b + 1] - ob), lane,
                                           stage[wib]);
         c = warp_sum(c);
-        if (lane == 0) out[i] = c;
+        // union_count = |A| + |B| - |A ∩ B|   (sorted_set.h:140)
+        if (lane == 0) out[i] = union_mode ? (unsigned long long)(off[a + 1] - oa) + (unsigned long long)(off[b + 1] - ob) - c : c;
     }
 }
 
@@ -76,6 +78,90 @@ k_pair_intersect(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, i
             c += __popc(mask);
         }
         if (!out_elems && lane == 0) counts[i] = c;
+    }
+}
+
+// Materialising difference N(a) \\ N(b), ascending (std::set_difference, sorted_set_operations.h:74-79): lanes walk A in
+// chunks of 32 and keep the elements that are NOT in B; same two-pass protocol as k_pair_intersect.
+__global__ void __launch_bounds__(256)
+k_pair_difference(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, int64_t np, const vid_t *__restrict__ pa,
+                  const vid_t *__restrict__ pb, int64_t *__restrict__ counts, const int64_t *__restrict__ out_off,
+                  vid_t *__restrict__ out_elems) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp; i < np; i += nwarps) {
+        const vid_t va = pa[i], vb = pb[i];
+        const vid_t *a = nbr + off[va], *b = nbr + off[vb];
+        const int na = (int)(off[va + 1] - off[va]), nb = (int)(off[vb + 1] - off[vb]);
+        const int64_t w = out_elems ? out_off[i] : 0;
+        int64_t c = 0;
+        for (int j0 = 0; j0 < na; j0 += 32) {
+            const int j = j0 + lane;
+            bool keep = false;
+            vid_t x = 0;
+            if (j < na) {
+                x = a[j];
+                const int lo = lower_bound_dev(b, nb, x);
+                keep = !(lo < nb && b[lo] == x);
+            }
+            const unsigned mask = __ballot_sync(0xffffffffu, keep);
+            if (out_elems && keep) out_elems[w + c + __popc(mask & ((1u << lane) - 1))] = x;
+            c += __popc(mask);
+        }
+        if (!out_elems && lane == 0) counts[i] = c;
+    }
+}
+
+// Materialising union, ascending (std::set_union, sorted_set_operations.h:30-35).  Every element knows its place in
+// the output without a merge: an element x of A sits after the |A<x| + |B<x| - |A∩B<x| smaller ones, i.e. at
+// j + lower_bound(B, x) - (common elements among A[0..j)); an element of B that is not in A likewise.
+__global__ void __launch_bounds__(256)
+k_pair_union(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, int64_t np, const vid_t *__restrict__ pa,
+             const vid_t *__restrict__ pb, int64_t *__restrict__ counts, const int64_t *__restrict__ out_off,
+             vid_t *__restrict__ out_elems) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp; i < np; i += nwarps) {
+        const vid_t va = pa[i], vb = pb[i];
+        const vid_t *a = nbr + off[va], *b = nbr + off[vb];
+        const int na = (int)(off[va + 1] - off[va]), nb = (int)(off[vb + 1] - off[vb]);
+        const int64_t w = out_elems ? out_off[i] : 0;
+        int common = 0;                      // common elements seen so far (running over the chunks)
+        for (int j0 = 0; j0 < na; j0 += 32) {
+            const int j = j0 + lane;
+            bool hit = false;
+            int lo = 0;
+            vid_t x = 0;
+            if (j < na) {
+                x = a[j];
+                lo = lower_bound_dev(b, nb, x);
+                hit = lo < nb && b[lo] == x;
+            }
+            const unsigned mask = __ballot_sync(0xffffffffu, hit);
+            if (out_elems && j < na) out_elems[w + j + lo - (common + __popc(mask & ((1u << lane) - 1)))] = x;
+            common += __popc(mask);
+        }
+        if (!out_elems) {
+            if (lane == 0) counts[i] = (int64_t)na + nb - common;
+            continue;
+        }
+        common = 0;
+        for (int t0 = 0; t0 < nb; t0 += 32) {
+            const int t = t0 + lane;
+            bool hit = false;
+            int lo = 0;
+            vid_t x = 0;
+            if (t < nb) {
+                x = b[t];
+                lo = lower_bound_dev(a, na, x);
+                hit = lo < na && a[lo] == x;
+            }
+            const unsigned mask = __ballot_sync(0xffffffffu, hit);
+            if (t < nb && !hit) out_elems[w + t + lo - (common + __popc(mask & ((1u << lane) - 1)))] = x;
+            common += __popc(mask);
+        }
     }
 }
 
@@ -169,7 +255,7 @@ void check_bad(DevBuf<int> &bad, const char *what) {
 
 }  // namespace
 
-void intersect_count_batch(Graph &g, int64_t np, const vid_t *a, const vid_t *b, uint64_t *out) {
+static void count_batch(Graph &g, int64_t np, const vid_t *a, const vid_t *b, uint64_t *out, bool union_mode) {
     if (np == 0) return;
     Runtime &r = rt();
     DevBuf<vid_t> da(np), db(np);
@@ -178,33 +264,65 @@ void intersect_count_batch(Graph &g, int64_t np, const vid_t *a, const vid_t *b,
     bad.zero();
     da.upload(a, np); db.upload(b, np);
     int grid = (int)std::min<int64_t>(ceil_div(np, kWarps), (int64_t)r.sm_count * 16);
-    k_pair_count<<<grid, kWarps * 32, 0, r.stream>>>(g.off.p, g.nbr.p, g.n, np, da.p, db.p, dout.p, bad.p); launched();
+    k_pair_count<<<grid, kWarps * 32, 0, r.stream>>>(g.off.p, g.nbr.p, g.n, np, da.p, db.p, dout.p, bad.p, union_mode ? 1 : 0);
+    launched();
     dout.download(reinterpret_cast<unsigned long long *>(out), np);
-    check_bad(bad, "intersect_count_batch");
+    check_bad(bad, union_mode ? "union_count_batch" : "intersect_count_batch");
+}
+void intersect_count_batch(Graph &g, int64_t np, const vid_t *a, const vid_t *b, uint64_t *out) {
+    count_batch(g, np, a, b, out, false);
+}
+void union_count_batch(Graph &g, int64_t np, const vid_t *a, const vid_t *b, uint64_t *out) {
+    count_batch(g, np, a, b, out, true);
 }
 
-void intersect_batch(Graph &g, int64_t np, const vid_t *a, const vid_t *b, int64_t *out_offsets, vid_t *out_elems,
-                     int64_t cap) {
+namespace {
+enum class SetOp { Intersect, Difference, Union };
+void set_batch(Graph &g, SetOp op, const char *what, int64_t np, const vid_t *a, const vid_t *b, int64_t *out_offsets,
+               vid_t *out_elems, int64_t cap) {
     out_offsets[0] = 0;
     if (np == 0) return;
     Runtime &r = rt();
     for (int64_t i = 0; i < np; ++i)
-        GMSB_REQUIRE(a[i] >= 0 && a[i] < g.n && b[i] >= 0 && b[i] < g.n, "intersect_batch: vertex id out of range");
+        GMSB_REQUIRE(a[i] >= 0 && a[i] < g.n && b[i] >= 0 && b[i] < g.n, std::string(what) + ": vertex id out of range");
     DevBuf<vid_t> da(np), db(np);
     DevBuf<int64_t> cnt(np + 1), pos(np + 1);
     cnt.zero();
     da.upload(a, np); db.upload(b, np);
-    int grid = (int)std::min<int64_t>(ceil_div(np, 8), (int64_t)r.sm_count * 16);
-    k_pair_intersect<<<grid, 256, 0, r.stream>>>(g.off.p, g.nbr.p, np, da.p, db.p, cnt.p, nullptr, nullptr); launched();
+    const int grid = (int)std::min<int64_t>(ceil_div(np, 8), (int64_t)r.sm_count * 16);
+    auto launch = [&](int64_t *counts, const int64_t *offs, vid_t *elems) {
+        if (op == SetOp::Intersect)
+            k_pair_intersect<<<grid, 256, 0, r.stream>>>(g.off.p, g.nbr.p, np, da.p, db.p, counts, offs, elems);
+        else if (op == SetOp::Difference)
+            k_pair_difference<<<grid, 256, 0, r.stream>>>(g.off.p, g.nbr.p, np, da.p, db.p, counts, offs, elems);
+        else
+            k_pair_union<<<grid, 256, 0, r.stream>>>(g.off.p, g.nbr.p, np, da.p, db.p, counts, offs, elems);
+        launched();
+    };
+    launch(cnt.p, nullptr, nullptr);
     exclusive_sum(cnt.p, pos.p, np + 1);
     pos.download(out_offsets, np + 1);
     const int64_t total = out_offsets[np];
     if (!out_elems) return;
-    GMSB_REQUIRE(cap >= total, "intersect_batch: output capacity too small");
+    GMSB_REQUIRE(cap >= total, std::string(what) + ": output capacity too small");
     if (total == 0) return;
     DevBuf<vid_t> elems(total);
-    k_pair_intersect<<<grid, 256, 0, r.stream>>>(g.off.p, g.nbr.p, np, da.p, db.p, nullptr, pos.p, elems.p); launched();
+    launch(nullptr, pos.p, elems.p);
     elems.download(out_elems, total);
+}
+}  // namespace
+
+void intersect_batch(Graph &g, int64_t np, const vid_t *a, const vid_t *b, int64_t *out_offsets, vid_t *out_elems,
+                     int64_t cap) {
+    set_batch(g, SetOp::Intersect, "intersect_batch", np, a, b, out_offsets, out_elems, cap);
+}
+void difference_batch(Graph &g, int64_t np, const vid_t *a, const vid_t *b, int64_t *out_offsets, vid_t *out_elems,
+                      int64_t cap) {
+    set_batch(g, SetOp::Difference, "difference_batch", np, a, b, out_offsets, out_elems, cap);
+}
+void union_batch(Graph &g, int64_t np, const vid_t *a, const vid_t *b, int64_t *out_offsets, vid_t *out_elems,
+                 int64_t cap) {
+    set_batch(g, SetOp::Union, "union_batch", np, a, b, out_offsets, out_elems, cap);
 }
 
 static void pair_similarity_device(Graph &g, int metric, int64_t np, const vid_t *da, const vid_t *db, double *out) {

@@ -131,6 +131,21 @@ public:
         check(gmsb_intersect_batch(h_, np, a.data(), b.data(), off.data(), el.data(), off[np]));
         return {std::move(off), std::move(el)};
     }
+    // N(a[i]) \ N(b[i]) and N(a[i]) ∪ N(b[i]) (SortedSet::difference / union_with, sorted_set.h:184-189,104-109), same layout
+    std::pair<std::vector<int64_t>, std::vector<NodeId>> difference(const std::vector<NodeId> &a,
+                                                                    const std::vector<NodeId> &b) const {
+        return two_pass(&gmsb_difference_batch, "difference", a, b);
+    }
+    std::pair<std::vector<int64_t>, std::vector<NodeId>> union_with(const std::vector<NodeId> &a,
+                                                                    const std::vector<NodeId> &b) const {
+        return two_pass(&gmsb_union_batch, "union_with", a, b);
+    }
+    std::vector<uint64_t> union_count(const std::vector<NodeId> &a, const std::vector<NodeId> &b) const {   // :140
+        if (a.size() != b.size()) throw std::invalid_argument("union_count: pair arrays differ in length");
+        std::vector<uint64_t> out(a.size());
+        check(gmsb_union_count_batch(h_, static_cast<int64_t>(a.size()), a.data(), b.data(), out.data()));
+        return out;
+    }
 
 private:
     gmsb_graph_t h_ = nullptr;
@@ -138,6 +153,17 @@ private:
     mutable std::vector<NodeId> nbr_;
     mutable bool mirrored_ = false;
 
+    using BatchFn = int (*)(gmsb_graph_t, int64_t, const int32_t *, const int32_t *, int64_t *, int32_t *, int64_t);
+    std::pair<std::vector<int64_t>, std::vector<NodeId>> two_pass(BatchFn fn, const char *what, const std::vector<NodeId> &a,
+                                                                  const std::vector<NodeId> &b) const {
+        if (a.size() != b.size()) throw std::invalid_argument(std::string(what) + ": pair arrays differ in length");
+        const int64_t np = static_cast<int64_t>(a.size());
+        std::vector<int64_t> off(a.size() + 1);
+        check(fn(h_, np, a.data(), b.data(), off.data(), nullptr, 0));
+        std::vector<NodeId> el(static_cast<size_t>(off[np]));
+        check(fn(h_, np, a.data(), b.data(), off.data(), el.data(), off[np]));
+        return {std::move(off), std::move(el)};
+    }
     int64_t slots() const { int64_t s = 0; check(gmsb_graph_num_slots(h_, &s)); return s; }
     void release() { if (h_) gmsb_graph_free(h_); h_ = nullptr; mirrored_ = false; }
     void swap(CudaSetGraph &o) {

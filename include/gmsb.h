@@ -148,7 +148,7 @@ GMSB_API int gmsb_tc_total_ex(gmsb_graph_t g, const gmsb_tc_options *opt, uint64
 /* TriangleCount::{Seq,Par}::vertex_count2 (= 2*t(u))    gms/algorithms/set_based/triangle_count/parallel/vertex.h:15-49 */
 GMSB_API int gmsb_tc_vertex2(gmsb_graph_t g, int64_t *out_n);
 
-/* ---- batched Set algebra (SortedSet::intersect_count / intersect on neighbourhoods) ----------------------------- */
+/* ---- batched Set algebra (SortedSet::intersect_count / intersect / difference / union on neighbourhoods) -------- */
 /* SortedSetBase::intersect_count                        gms/representations/sets/sorted_set.h:176-182
  * out[i] = |N(a[i]) ∩ N(b[i])| */
 GMSB_API int gmsb_intersect_count_batch(gmsb_graph_t g, int64_t npairs, const int32_t *a, const int32_t *b, uint64_t *out);
@@ -156,6 +156,18 @@ GMSB_API int gmsb_intersect_count_batch(gmsb_graph_t g, int64_t npairs, const in
  * two-pass: out_offsets[npairs+1] always written; out_elems may be NULL to size the result first. */
 GMSB_API int gmsb_intersect_batch(gmsb_graph_t g, int64_t npairs, const int32_t *a, const int32_t *b, int64_t *out_offsets,
                          int32_t *out_elems, int64_t out_capacity);
+
+/* SortedSetBase::difference(const Set&)                 gms/representations/sets/sorted_set.h:184-189
+ * N(a[i]) \ N(b[i]), ascending; same two-pass protocol as gmsb_intersect_batch. */
+GMSB_API int gmsb_difference_batch(gmsb_graph_t g, int64_t npairs, const int32_t *a, const int32_t *b, int64_t *out_offsets,
+                          int32_t *out_elems, int64_t out_capacity);
+/* SortedSetBase::union_with(const Set&)                 gms/representations/sets/sorted_set.h:104-109
+ * N(a[i]) ∪ N(b[i]), ascending; same two-pass protocol. */
+GMSB_API int gmsb_union_batch(gmsb_graph_t g, int64_t npairs, const int32_t *a, const int32_t *b, int64_t *out_offsets,
+                     int32_t *out_elems, int64_t out_capacity);
+/* SortedSetBase::union_count                            gms/representations/sets/sorted_set.h:140
+ * out[i] = |N(a[i]) ∪ N(b[i])| */
+GMSB_API int gmsb_union_count_batch(gmsb_graph_t g, int64_t npairs, const int32_t *a, const int32_t *b, uint64_t *out);
 
 /* ---- vertex similarity ------------------------------------------------------------------------------------------------ */
 /* GMS::VertexSim::Metric                                gms/algorithms/set_based/vertex_similarity/vertex_similarity.h:18 */

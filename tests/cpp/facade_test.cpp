@@ -76,6 +76,12 @@ static int run() {
     EXPECT(sets.intersect_count({8}, {9})[0] == 3);
     auto is = sets.intersect({8, 9}, {9, 8});
     EXPECT((is.second == std::vector<NodeId>{3, 4, 5, 3, 4, 5}));
+    // testing/sets.cpp difference / union KATs on the same sets: {1..5}\{3..7} = {1,2}, union = {1..7}
+    auto df = sets.difference({8, 9}, {9, 8});
+    EXPECT((df.second == std::vector<NodeId>{1, 2, 6, 7}) && df.first[1] == 2);
+    auto un = sets.union_with({8}, {9});
+    EXPECT((un.second == std::vector<NodeId>{1, 2, 3, 4, 5, 6, 7}));
+    EXPECT(sets.union_count({8, 8}, {9, 8}) == (std::vector<uint64_t>{7, 5}));
     // generated graph: kronecker-12 (golden: 483489 triangles, 4021397 4-cliques)
     CudaSetGraph kron = CudaSetGraph::Kronecker(12);
     EXPECT(TriangleCount::Par::count_total<CudaSetGraph>(kron) == 483489);

@@ -199,6 +199,13 @@ def test_set_kats_through_neighbourhoods(gms, golden):
         for i, kat in enumerate(golden["sets"]):
             assert cnt[i] == len(kat["intersect"])
             assert elems[off[i]:off[i + 1]].tolist() == kat["intersect"]
+    # union / difference / union_count of the same KAT sets (testing/sets.cpp union* / difference* cases)
+    uoff, uel = g.union_batch(a, b)
+    doff, del_ = g.difference_batch(a, b)
+    ucnt = g.union_count_batch(a, b)
+    for i, kat in enumerate(golden["sets"]):            # golden values produced by the reference's SortedSet
+        assert uel[uoff[i]:uoff[i + 1]].tolist() == kat["union"] and ucnt[i] == kat["union_count"]
+        assert del_[doff[i]:doff[i + 1]].tolist() == kat["difference"]
 
 
 @pytest.mark.parametrize("seed", range(3))
@@ -216,6 +223,15 @@ def test_pair_ops_against_oracle(gms, orc, seed):
     for i in range(500):
         ref_i = np.intersect1d(onbr[ooff[a[i]]:ooff[a[i] + 1]], onbr[ooff[b[i]]:ooff[b[i] + 1]])
         assert elems[off[i]:off[i + 1]].tolist() == ref_i.tolist()
+    # materialising difference / union and union_count against the oracle's restatement of sorted_set.h:104-140,184-189
+    doff, delems = g.difference_batch(a[:500], b[:500])
+    uoff, uelems = g.union_batch(a[:500], b[:500])
+    ucnt = g.union_count_batch(a[:500], b[:500])
+    for i in range(500):
+        la, lb = onbr[ooff[a[i]]:ooff[a[i] + 1]], onbr[ooff[b[i]]:ooff[b[i] + 1]]
+        assert delems[doff[i]:doff[i + 1]].tolist() == orc.difference(la, lb).tolist()
+        assert uelems[uoff[i]:uoff[i + 1]].tolist() == orc.union(la, lb).tolist()
+        assert int(ucnt[i]) == orc.union_count(la, lb) == uoff[i + 1] - uoff[i]
     for mname in EXACT_METRICS:
         assert g.pair_similarity(mname, a, b).tobytes() == o.pair_similarity(mname, a, b).tobytes(), mname
         assert g.edge_similarity(mname).tobytes() == o.edge_similarity(mname).tobytes(), mname
