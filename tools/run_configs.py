@@ -57,7 +57,7 @@ def main():
             for k in range(3, args.kmax + 1):
                 if prev is not None and prev * 50 > args.kcap_seconds:
                     emit(config="cfg3-kclique", scale=args.scale22, k=k, skipped=f"predicted > {args.kcap_seconds}s "
-                         f"(previous k took {prev:.1f}s; cost grew ~50x from k=5 to k=6 at scale 22)")
+                         f"(previous k took {prev:.1f}s; the search grows ~50x per k at scale 22, see DESIGN.md section 3)")
                     prev = prev * 50
                     continue
                 t0 = time.time()
