@@ -78,16 +78,14 @@ __device__ __forceinline__ u64 lane_tasks(const u64 *cm, int pitch, unsigned t_e
 
 // ---- third level: per-warp compact matrix ------------------------------------------------------------------------------
 // With four or more vertices still to pick below a member a of cm, the search below a runs in a matrix of its own:
-// the WARP re-indexes row a (<= 128 members) into M3 (rows of 1-2 words instead of up to 8) and its lanes pull M3's
+// the WARP re-indexes row a (<= kC3Max = 192 members) into M3 (rows of 1-3 words instead of up to 8) and its lanes pull M3's
 // tasks from a warp-local ticket.  Deep in the tree the sets hold 3-5 members per word of the parent's index space, so
 // every AND + popcount there is mostly zeros; one more re-indexing halves to quarters the words per step and fills
 // them.  Rows that are too large for M3 are put on a list and searched in cm afterwards by all lanes of the CTA.
-// Used by the 129..512 classes (measured at scale 22: k = 6 mid8 4.53 -> 3.56 s; k = 7 mid8 -18 %, mid4 -19 %).  In the
+// Used by the 129..512 classes (scale 22, k = 6: the <= 512 class 4.53 -> 3.43 s; scale 20, k = 7: 66.9 -> 51.5 s when M3 grew from 128 to 192 members).  In the
 // d+ > 512 kernel it was NOT a win (k = 7: +18 %): rows of M2 mostly exceed 128 members, a warp's 32 lanes drain at
 // the end of every member, and the extra live state pushed that kernel into register spills — it deals every task of
 // M2 to the lanes of the whole CTA instead.
-constexpr int kC3Max = 128;
-constexpr int kP3 = 3;                       // pitch of M3 (2 valid words, odd)
 struct WarpBox {
     u64 m3[kC3Max * kP3];
     u64 set[8];
@@ -133,15 +131,17 @@ __device__ u64 warp_tasks(const u64 *cm, int pitch, int nw, int c, int need, uns
             if ((box->set[p >> 6] >> (p & 63)) & 1ull)
                 box->list[compact_index(box->set, box->prefix, p)] = (unsigned short)p;
         __syncwarp();
-        const int nw3 = c3 <= 64 ? 1 : 2;
+        const int nw3 = (c3 + 63) >> 6;              // 1..3 words per row of M3
         for (int m = lane; m < c3; m += 32) {
             const int pa = box->list[m];
             compact_row(box->set, box->prefix, nw, cm + (size_t)pa * pitch, pa, box->m3 + (size_t)m * kP3, nw3);
         }
         __syncwarp();
         const int sl = split_for(c3, 32);
-        total += nw3 == 1 ? lane_tasks<1>(box->m3, kP3, (unsigned)c3 << sl, need - 1, sl, &box->counter, lane, nullptr)
-                          : lane_tasks<2>(box->m3, kP3, (unsigned)c3 << sl, need - 1, sl, &box->counter, lane, nullptr);
+        const unsigned t3 = (unsigned)c3 << sl;
+        total += nw3 == 1   ? lane_tasks<1>(box->m3, kP3, t3, need - 1, sl, &box->counter, lane, nullptr)
+                 : nw3 == 2 ? lane_tasks<2>(box->m3, kP3, t3, need - 1, sl, &box->counter, lane, nullptr)
+                            : lane_tasks<3>(box->m3, kP3, t3, need - 1, sl, &box->counter, lane, nullptr);
         __syncwarp();
     }
     return total;

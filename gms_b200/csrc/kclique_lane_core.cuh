@@ -27,6 +27,8 @@ constexpr int kCMax = 512;         // members of a compact sub-problem (9-bit me
 constexpr int kPathBits = 9;
 constexpr int kPathLevels = 7;     // 7 x 9 bits in one 64-bit register
 constexpr int kMaxNeed = kPathLevels + 2;   // deepest stored level is need - 3
+constexpr int kC3Max = 192;        // members of a per-warp third-level matrix (kclique_lane.cuh: warp_tasks)
+constexpr int kP3 = 3;             // its pitch: up to 3 valid 64-bit words per row
 
 GMSB_HD int popc64(u64 x) {
 #if defined(__CUDA_ARCH__)

@@ -158,7 +158,7 @@ int main() {
     // 3. third level (kclique_lane.cuh: warp_tasks): below a member a whose row has <= 128 members the search runs in
     //    a re-indexed matrix M3 (pitch 3) with need-1; larger rows are searched in cm as 64 residue-class tasks
     for (int c : {90, 200, 220, 400, 512}) {
-        auto adj = c == 220 ? random_dag(c, 0.8, rng, false)          // rows of up to ~175 members: too large for M3
+        auto adj = c == 220 ? random_dag(c, 0.95, rng, false)         // rows of up to ~210 members: too large for M3
                             : random_dag(c, c <= 200 ? 0.6 : 0.3, rng, true);
         const int nw = bucket(c), pitch = pitch_for(nw);
         std::vector<u64> cm((size_t)c * pitch, 0);
@@ -177,7 +177,7 @@ int main() {
                 int prefix[8] = {0}, c3 = 0;
                 for (int w = 0; w < nw; ++w) { prefix[w] = c3; c3 += popc64(row[w]); }
                 if (c3 < need - 1) continue;
-                if (c3 > 128) {
+                if (c3 > kC3Max) {
                     ++big;
                     for (unsigned st = 0; st < 64; ++st) got += run_task_any(nw, cm, pitch, need, ((unsigned)a << 6) | st, 6);
                     continue;
@@ -186,11 +186,11 @@ int main() {
                 std::vector<int> list(c3);
                 for (int p = 0; p < nw * 64; ++p)
                     if ((row[p >> 6] >> (p & 63)) & 1) list[compact_index(row, prefix, p)] = p;
-                const int nw3 = c3 <= 64 ? 1 : 2;
-                std::vector<u64> m3((size_t)c3 * 3, ~0ull);
+                const int nw3 = (c3 + 63) >> 6;
+                std::vector<u64> m3((size_t)c3 * kP3, ~0ull);
                 for (int m = 0; m < c3; ++m)
-                    compact_row(row, prefix, nw, cm.data() + (size_t)list[m] * pitch, list[m], m3.data() + (size_t)m * 3, nw3);
-                got += run_any(nw3, m3, 3, c3, need - 1, 3);
+                    compact_row(row, prefix, nw, cm.data() + (size_t)list[m] * pitch, list[m], m3.data() + (size_t)m * kP3, nw3);
+                got += run_any(nw3, m3, kP3, c3, need - 1, 3);
             }
             ++checks;
             if (got != want) { ++fails; std::printf("FAIL third-level c=%d need=%d got=%llu want=%llu\n", c, need, got, want); }
