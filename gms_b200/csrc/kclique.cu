@@ -583,6 +583,29 @@ uint64_t count_on_dag(int64_t n, int64_t m, const eid_t *off, const vid_t *nbr, 
                 cudaEventRecord(ev[nev++], r.stream);
             };
             mark();
+            // The five class kernels are independent (own ticket, atomics on one total).  Each goes to its own stream
+            // so that the CTAs of the next class fill the SMs that the previous class's last items leave idle; with
+            // the sub-problems split over several GPUs those tails are a visible share of a launch.  (Serial when
+            // tracing, so that the per-class times mean something.)
+            struct AuxStreams {
+                cudaStream_t s[4] = {nullptr, nullptr, nullptr, nullptr};
+                cudaEvent_t ev = nullptr;
+                ~AuxStreams() {
+                    for (auto st : s) if (st) cudaStreamDestroy(st);
+                    if (ev) cudaEventDestroy(ev);
+                }
+            } auxs;
+            cudaStream_t (&aux)[4] = auxs.s;
+            cudaEvent_t &ready = auxs.ev;
+            if (!trace) {
+                GMSB_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+                GMSB_CUDA(cudaEventRecord(ready, r.stream));
+                for (auto &st : aux) {
+                    GMSB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+                    GMSB_CUDA(cudaStreamWaitEvent(st, ready, 0));
+                }
+            }
+            int next_aux = 0;
             if (n_huge) {           // d+ > 512: CTA-wide top of the tree, compact matrices below
                 exclusive_sum(parts.p, item_base.p, n_huge + 1);
                 const int64_t n_items = item_base.get(n_huge);
@@ -614,7 +637,8 @@ uint64_t count_on_dag(int64_t n, int64_t m, const eid_t *off, const vid_t *nbr, 
                 GMSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, block, dyn));
                 GMSB_REQUIRE(resident >= 1, "kclique_count: kernel does not fit on an SM");
                 const int grid = (int)std::min<int64_t>(cnt, (int64_t)r.sm_count * resident);
-                kern<<<grid, block, dyn, r.stream>>>(vb.p + first, cnt, off, nbr, k, total.p, ticket, pi, P, flags);
+                cudaStream_t st = trace ? r.stream : aux[next_aux++];
+                kern<<<grid, block, dyn, st>>>(vb.p + first, cnt, off, nbr, k, total.p, ticket, pi, P, flags);
                 launched();
             };
             auto mid_marked = [&](auto kern, int block, bool boxes, int64_t first, int64_t cnt, unsigned int *ticket) {
@@ -625,6 +649,12 @@ uint64_t count_on_dag(int64_t n, int64_t m, const eid_t *off, const vid_t *nbr, 
             mid_marked(lane::k_kclique_lane_mid<4, 256, 4>, 256, true, bound[1], bound[2] - bound[1], tickets.p + 2);
             mid_marked(lane::k_kclique_lane_mid<2, 128, 8>, 128, false, bound[2], bound[3] - bound[2], tickets.p + 3);
             mid_marked(lane::k_kclique_lane_mid<1, 128, 8>, 128, false, bound[3], nb - bound[3], tickets.p + 4);
+            if (!trace) {
+                for (auto &st : aux) {           // join: the library stream continues after every class
+                    GMSB_CUDA(cudaEventRecord(ready, st));
+                    GMSB_CUDA(cudaStreamWaitEvent(r.stream, ready, 0));
+                }
+            }
             GMSB_CUDA(cudaStreamSynchronize(r.stream));
             if (trace) {
                 static const char *names[5] = {"huge(d+>512)", "mid8(<=512)", "mid4(<=256)", "mid2(<=128)", "mid1(<=64)"};
