@@ -179,6 +179,7 @@ class CpuLib:
                 "clique_counts_pivot": (None, [C.c_void_p, C.c_int, np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")]),
                 "tc_bytes": (None, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                     C.POINTER(C.c_int64)]),
+                "kclique_bytes": (C.c_uint64, [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]),
             })
         else:
             sig.update({"degeneracy_danisch_heap": (None, [C.c_void_p, _i32p]),
@@ -296,6 +297,12 @@ class CpuLib:
 
     def core_number_of_rank(self, g, rank):
         return int(self._f("core_number_of_rank")(g.h, np.ascontiguousarray(rank, np.int32)))
+
+    def kclique_bytes(self, dag, k):
+        """(B_k, count): algorithmic bytes of the set-algebra clique recursion on the DAG and the count."""
+        cnt = C.c_uint64(0)
+        b = self._f("kclique_bytes")(dag.h, k, C.byref(cnt))
+        return int(b), int(cnt.value)
 
     def tc_bytes(self, g):
         bt, br, mx = C.c_uint64(0), C.c_uint64(0), C.c_int64(0)

@@ -326,6 +326,38 @@ uint64_t dag_cliques_rec(const Graph &g, int left, const vid *s, int64_t ns, std
     }
     return c;
 }
+// Algorithmic bytes of that recursion (B_k): every intersection S ∩ N+(v) it performs streams
+// 4·(|S| + d+(v)) bytes.  Same walk as dag_cliques_rec with the byte counter added (the pruned branches have already
+// paid for the intersection that pruned them).
+uint64_t dag_clique_bytes_rec(const Graph &g, int left, const vid *s, int64_t ns, std::vector<std::vector<vid>> &scratch,
+                              uint64_t &bytes) {
+    if (left == 1) return (uint64_t)ns;
+    uint64_t c = 0;
+    std::vector<vid> &buf = scratch[left];
+    if ((int64_t)buf.size() < ns) buf.resize(ns);
+    for (int64_t i = 0; i < ns; ++i) {
+        vid v = s[i];
+        bytes += 4 * (uint64_t)(ns + g.deg(v));
+        if (left == 2) { c += isect_count(s, s + ns, g.begin(v), g.end(v)); continue; }
+        int64_t k = isect_write(s, s + ns, g.begin(v), g.end(v), buf.data());
+        if (k >= left - 1) c += dag_clique_bytes_rec(g, left - 1, buf.data(), k, scratch, bytes);
+    }
+    return c;
+}
+uint64_t dag_clique_bytes(const Graph &g, int k, uint64_t *count_out) {
+    uint64_t total = 0, bytes = 0;
+    if (k >= 3) {
+        #pragma omp parallel reduction(+:total, bytes)
+        {
+            std::vector<std::vector<vid>> scratch(k + 1);
+            #pragma omp for schedule(dynamic, 16)
+            for (int64_t u = 0; u < g.n; ++u)
+                total += dag_clique_bytes_rec(g, k - 1, g.begin((vid)u), g.deg((vid)u), scratch, bytes);
+        }
+    }
+    if (count_out) *count_out = k >= 3 ? total : (k == 2 ? (uint64_t)g.off[g.n] : (uint64_t)g.n);
+    return bytes;
+}
 uint64_t dag_cliques(const Graph &g, int k) {
     if (k == 1) return (uint64_t)g.n;
     if (k == 2) return (uint64_t)g.off[g.n];
@@ -621,6 +653,7 @@ double orc_kclique_timed(void *h, int k, int mode, uint64_t *out) {
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 uint64_t orc_clique_count_set_based(void *h, int k) { return ordered_cliques(*G(h), k); }
+uint64_t orc_kclique_bytes(void *h, int k, uint64_t *count_out) { return dag_clique_bytes(*G(h), k, count_out); }
 void orc_clique_counts_pivot(void *h, int kmax, uint64_t *out) { clique_counts_pivot(*G(h), kmax, out); }
 
 double orc_vertex_similarity(void *h, int metric, int32_t a, int32_t b) { return similarity(*G(h), metric, a, b); }

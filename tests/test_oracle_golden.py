@@ -152,3 +152,19 @@ def test_oracle_sets_match_reference_random(orc, ref):
         assert orc.difference(a, b).tolist() == ref.difference(a, b).tolist()
         x = int(rng.integers(0, 80))
         assert orc.contains(a, x) == ref.contains(a, x)
+
+
+def test_clique_recursion_bytes(orc, golden):
+    """B_k: the instrumented recursion counts the same cliques, and its k = 3 bytes are B_TC."""
+    g = orc.generate(12)
+    dag = g.induce_directed(g.degree_order(True))
+    rec = golden["generated"]["kronecker-12"]["kclique"]
+    b_tc, _, _ = orc.tc_bytes(g)
+    prev = 0
+    for k in (3, 4, 5):
+        b, c = orc.kclique_bytes(dag, k)
+        assert c == rec[str(k)] == dag.kclique(k)
+        assert b > prev
+        prev = b
+        if k == 3:
+            assert b == b_tc
