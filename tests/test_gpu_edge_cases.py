@@ -152,3 +152,26 @@ def test_degenerate_clique_sizes_and_errors(gms):
         dag.kclique_count_ordered(3)        # ordered convention is defined on the undirected graph
     with pytest.raises(gms.GmsbError):
         g.pair_similarity("jaccard", [0], [99])
+
+
+def test_large_host_csr_sorted_unsorted_and_malformed(gms):
+    """A host CSR of 31 M slots through gmsb_graph_from_csr: sorted lists, a few reversed lists (the one streaming check
+    finds them and only then a sort is paid for), and a malformed id at the very end."""
+    s, d = gms.generate_rmat(20)
+    g = gms.Graph.from_edgelist(s, d, True)
+    off, nbr = g.export_csr()
+    assert len(nbr) >= 1 << 24
+    assert gms.Graph.from_csr(off, nbr).tc_total() == 423625371            # SURVEY.md 8c, kronecker-20
+    rev = nbr.copy()
+    for u in (0, 1, 2, len(off) // 2, len(off) - 2):                       # a few lists reversed, one in every region
+        rev[off[u]:off[u + 1]] = rev[off[u]:off[u + 1]][::-1]
+    big = int(np.argmax(np.diff(off)))
+    rev[off[big]:off[big + 1]] = rev[off[big]:off[big + 1]][::-1]
+    g2 = gms.Graph.from_csr(off, rev)
+    assert g2.tc_total() == 423625371
+    o2, n2 = g2.export_csr()
+    assert (o2 == off).all() and (n2 == nbr).all()
+    bad = nbr.copy()
+    bad[-1] = g.n                                                           # id out of range in the last slot
+    with pytest.raises(gms.GmsbError):
+        gms.Graph.from_csr(off, bad)
