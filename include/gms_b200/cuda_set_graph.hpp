@@ -9,6 +9,7 @@
 #pragma once
 #include <algorithm>
 #include <cstdint>
+#include <iostream>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -61,17 +62,39 @@ public:
 
     // SetGraph<Set>::FromCGraph (set_graph.h:87-89): any graph type with num_nodes(), out_degree(u), out_neigh(u)
     // and directed(); the lists must be ascending and duplicate-free, as Builder::SquishGraph leaves them.
-    template <class CGraph>
+    // RemoveIsolated = true mirrors cgraph_to_neighborhoods_remove_isolated (set_graph.h:190-232): vertices without
+    // neighbours are dropped, the others keep their order and are renumbered 0..n'-1 (and the reference's notice is
+    // printed); per-vertex results are then indexed by the new ids, exactly as in the reference.
+    template <class CGraph, bool RemoveIsolated = false>
     static CudaSetGraph FromCGraph(const CGraph &g) {
         const int64_t n = g.num_nodes();
-        std::vector<int64_t> off(static_cast<size_t>(n) + 1, 0);
-        for (int64_t u = 0; u < n; ++u) off[u + 1] = off[u] + static_cast<int64_t>(g.out_degree(static_cast<NodeId>(u)));
-        std::vector<NodeId> nbr(static_cast<size_t>(off[n]));
-        for (int64_t u = 0; u < n; ++u) {
-            int64_t p = off[u];
-            for (NodeId v : g.out_neigh(static_cast<NodeId>(u))) nbr[p++] = v;
+        std::vector<NodeId> label;
+        int64_t isolated = 0;
+        if (RemoveIsolated) {
+            label.resize(static_cast<size_t>(n));
+            for (int64_t u = 0; u < n; ++u) {
+                if (g.out_degree(static_cast<NodeId>(u)) == 0) { label[u] = -1; ++isolated; }
+                else label[u] = static_cast<NodeId>(u - isolated);
+            }
         }
-        return FromCSR(n, off.data(), nbr.data(), g.directed());
+        const bool relabel = RemoveIsolated && isolated > 0;
+        const int64_t kept = n - isolated;
+        std::vector<int64_t> off(static_cast<size_t>(kept) + 1, 0);
+        for (int64_t u = 0, k = 0; u < n; ++u) {
+            if (relabel && label[u] < 0) continue;
+            off[k + 1] = off[k] + static_cast<int64_t>(g.out_degree(static_cast<NodeId>(u)));
+            ++k;
+        }
+        std::vector<NodeId> nbr(static_cast<size_t>(off[kept]));
+        for (int64_t u = 0, k = 0; u < n; ++u) {
+            if (relabel && label[u] < 0) continue;
+            int64_t p = off[k++];
+            for (NodeId v : g.out_neigh(static_cast<NodeId>(u))) nbr[p++] = relabel ? label[v] : v;
+        }
+        if (relabel)
+            std::cout << "Removed " << isolated
+                      << " isolated vertices from the graph, the graph got relabeled and shrunk!" << std::endl;
+        return FromCSR(kept, off.data(), nbr.data(), g.directed());
     }
     static CudaSetGraph FromCSR(int64_t n, const int64_t *offsets, const NodeId *nbrs, bool directed = false) {
         gmsb_graph_t h = nullptr;

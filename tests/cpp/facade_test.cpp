@@ -45,6 +45,16 @@ static int run() {
     EXPECT(g.out_degree(1) == 3 && g.out_neigh(1).cardinality() == 3 && *g.out_neigh(1).begin() == 0);
     CudaSetGraph c = g.clone();
     EXPECT(TriangleCount::Par::count_total<CudaSetGraph>(c) == 3);
+    // FromCGraph<CGraph, RemoveIsolated = true> (set_graph.h:190-232, testing/set_graph.cpp): vertex 4 of triangles_3 has
+    // no neighbours; it is dropped and 5..9 become 4..8, per-vertex results follow the new ids
+    CudaSetGraph shrunk = CudaSetGraph::FromCGraph<CudaSetGraph, true>(g);
+    EXPECT(shrunk.num_nodes() == 9 && shrunk.num_edges() == 11);
+    EXPECT(TriangleCount::Par::count_total<CudaSetGraph>(shrunk) == 3);
+    TriangleCount::Par::vertex_count2<CudaSetGraph>(shrunk, counts);
+    EXPECT((counts == std::vector<int64_t>{2, 4, 4, 2, 2, 2, 2, 0, 0}));
+    EXPECT(*shrunk.out_neigh(4).begin() == 5);                      // old 5 -> {6, 7}, now 4 -> {5, 6}
+    CudaSetGraph same = CudaSetGraph::FromCGraph<CudaSetGraph, true>(shrunk);    // nothing to remove: unchanged
+    EXPECT(same.num_nodes() == 9 && TriangleCount::Par::count_total<CudaSetGraph>(same) == 3);
     // FromCGraph from a host CSR type
     HostCsr h;
     h.off = {0, 2, 4, 6};
