@@ -96,6 +96,28 @@ public:
                       << " isolated vertices from the graph, the graph got relabeled and shrunk!" << std::endl;
         return FromCSR(kept, off.data(), nbr.data(), g.directed());
     }
+    // SetGraph<Set>::FromEL (set_graph.h:54-78): neighbourhood of u = the second entries of the pairs whose first is u;
+    // the list is sorted in place unless is_sorted, and — like the reference — NOT symmetrised.  The device handle
+    // needs to know whether the result is symmetric (SetGraph::directed() computes that on demand, set_graph.h:128-137).
+    template <class EL>
+    static CudaSetGraph FromEL(EL &edge_list, size_t num_nodes, bool is_sorted) {
+        if (!is_sorted) std::sort(edge_list.begin(), edge_list.end());
+        std::vector<int64_t> off(num_nodes + 1, 0);
+        std::vector<NodeId> nbr;
+        nbr.reserve(edge_list.size());
+        auto it = edge_list.begin();
+        for (size_t u = 0; u < num_nodes; ++u) {
+            while (it != edge_list.end() && static_cast<size_t>(it->first) == u) { nbr.push_back(it->second); ++it; }
+            off[u + 1] = static_cast<int64_t>(nbr.size());
+        }
+        bool directed = false;
+        for (size_t u = 0; u < num_nodes && !directed; ++u)
+            for (int64_t p = off[u]; p < off[u + 1] && !directed; ++p) {
+                const NodeId v = nbr[p];
+                directed = !std::binary_search(nbr.begin() + off[v], nbr.begin() + off[v + 1], static_cast<NodeId>(u));
+            }
+        return FromCSR(static_cast<int64_t>(num_nodes), off.data(), nbr.data(), directed);
+    }
     static CudaSetGraph FromCSR(int64_t n, const int64_t *offsets, const NodeId *nbrs, bool directed = false) {
         gmsb_graph_t h = nullptr;
         check(gmsb_graph_from_csr(n, offsets, nbrs, directed ? 1 : 0, &h));

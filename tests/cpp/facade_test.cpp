@@ -55,6 +55,23 @@ static int run() {
     EXPECT(*shrunk.out_neigh(4).begin() == 5);                      // old 5 -> {6, 7}, now 4 -> {5, 6}
     CudaSetGraph same = CudaSetGraph::FromCGraph<CudaSetGraph, true>(shrunk);    // nothing to remove: unchanged
     EXPECT(same.num_nodes() == 9 && TriangleCount::Par::count_total<CudaSetGraph>(same) == 3);
+    // testing/set_graph.cpp:69-114 — FromCGraph default / RemoveIsolated on the edge 0-2 (vertex 1 isolated), Clone
+    {
+        CudaSetGraph with_iso = from_pairs({{0, 2}});
+        CudaSetGraph d = CudaSetGraph::FromCGraph(with_iso);
+        EXPECT(d.num_nodes() == 3 && d.out_degree(1) == 0 && *d.out_neigh(0).begin() == 2 && *d.out_neigh(2).begin() == 0);
+        CudaSetGraph r = CudaSetGraph::FromCGraph<CudaSetGraph, true>(with_iso);
+        EXPECT(r.num_nodes() == 2 && *r.out_neigh(0).begin() == 1 && *r.out_neigh(1).begin() == 0);
+        CudaSetGraph cl = r.clone();
+        EXPECT(cl.num_nodes() == 2 && cl.out_degree(0) == 1 && *cl.out_neigh(1).begin() == 0);
+        // FromEL (set_graph.h:54-78): not symmetrised, sorted on request
+        std::vector<std::pair<NodeId, NodeId>> el = {{2, 0}, {0, 2}, {0, 1}, {1, 0}, {1, 2}, {2, 1}};
+        CudaSetGraph fe = CudaSetGraph::FromEL(el, 3, false);
+        EXPECT(fe.num_nodes() == 3 && !fe.directed() && fe.out_degree(0) == 2 && *fe.out_neigh(0).begin() == 1);
+        EXPECT(TriangleCount::Par::count_total<CudaSetGraph>(fe) == 1);
+        std::vector<std::pair<NodeId, NodeId>> one_way = {{0, 1}, {0, 2}, {1, 2}};
+        EXPECT(CudaSetGraph::FromEL(one_way, 3, true).directed());
+    }
     // FromCGraph from a host CSR type
     HostCsr h;
     h.off = {0, 2, 4, 6};
