@@ -16,7 +16,9 @@ symmetric CSR on the GPU (radix sort), keep a copy of the CSR in PINNED host mem
   * `cpu_baseline` (N=1): the reference's own Par::count_total inner loop (oracle/_ref, else the oracle port) on a
                bounded sample of the same graph, all host threads;
   * `kclique` : the other half of BASELINE.json's metric — k-clique counts/s for k = 4,5,6 on configs[2]
-               (Kronecker scale-22), sub-problems dealt over the ranks, one all-reduce (--kclique '' skips it).
+               (Kronecker scale-22), sub-problems dealt over the ranks, one all-reduce (--kclique '' skips it); at N=1
+               with `kclique.cpu_baseline`: the reference's Par::EP_kclisting on all host threads on Kronecker
+               scale-16 and our kernels on that same graph.
 N>1 (torchrun): every rank holds the whole CSR, counts share rank/N of the schedule, one all-reduce sums the counts;
 time = max over ranks.  In the e2e leg rank r uploads slice r/N of the host CSR and the slices are all-gathered over
 NVLink, so h2d_bytes_per_step is still the whole CSR once (summed over ranks).
@@ -189,7 +191,42 @@ def run_kclique(args, G, gd, rank, world, dev):
                        "degree-oriented DAG, graph replicated, per-vertex sub-problems dealt over the ranks",
            "metric": "kclique_counts_per_sec", "unit": "cliques/s", "n_gpus": world, "results": rows}
     g.free()
+    # the reference's Par::EP_kclisting beside it (rank 0, N=1): bounded by running it on a smaller graph of the same
+    # family, with our kernels timed on that same graph for a like-for-like ratio
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            out["cpu_baseline"] = kclique_cpu_baseline(args, G)
+        except Exception as ex:      # reported, never required
+            out["cpu_baseline"] = {"kind": "unavailable", "sample": str(ex)}
     return out
+
+
+def kclique_cpu_baseline(args, G, scale=16):
+    lib, kind = cpu_lib()
+    cores = lib.max_threads()
+    cg = lib.generate(scale, 16, False)
+    dag = cg.induce_directed(cg.degree_order(True))
+    src, dst = G.generate_rmat(scale)
+    g = G.Graph.from_edgelist(src, dst, True)
+    g.kclique_count(3)
+    rows = []
+    for k in [int(x) for x in args.kclique.split(",")]:
+        sec, cnt = dag.kclique_timed(k, 2)                     # mode 2 = edge-parallel (EP_kclisting)
+        best = None
+        for _ in range(3):
+            t0 = time.perf_counter()
+            ours = g.kclique_count(k)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        assert ours == cnt, (k, ours, cnt)
+        rows.append({"k": k, "count": cnt, "cpu_seconds": sec, "cpu_cliques_per_s": cnt / sec, "gpu_seconds": best,
+                     "gpu_cliques_per_s": cnt / best})
+        log(f"[cpu_baseline] kclique k={k} scale {scale}: {kind} {sec:.2f}s on {cores} threads, GPU {best * 1e3:.2f} ms")
+    g.free()
+    return {"kind": kind, "cores": cores, "unit": "cliques/s",
+            "sample": f"Kronecker scale-{scale} edge factor 16 (same generator), degree-oriented DAG, "
+                      f"KClique::Par::EP_kclisting on all host threads; gpu_seconds = gmsb_kclique_count on the same graph",
+            "results": rows}
 
 
 def run_ours(args):
