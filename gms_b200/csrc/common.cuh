@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -110,6 +111,28 @@ struct DevTimer {
         float t = 0;
         cudaEventElapsedTime(&t, a, b);
         return t;
+    }
+};
+
+// GMSB_TC_TRACE=1: device time of every phase of the representation build on stderr (profiling aid)
+struct PhaseTrace {
+    bool on;
+    cudaEvent_t last = nullptr;
+    explicit PhaseTrace(const char *env) : on(std::getenv(env) != nullptr) {
+        if (on) { cudaEventCreate(&last); cudaEventRecord(last, rt().stream); }
+    }
+    ~PhaseTrace() { if (last) cudaEventDestroy(last); }
+    void mark(const char *what) {
+        if (!on) return;
+        cudaEvent_t now;
+        cudaEventCreate(&now);
+        cudaEventRecord(now, rt().stream);
+        cudaEventSynchronize(now);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, last, now);
+        std::fprintf(stderr, "[gmsb trace] %-28s %8.3f ms\n", what, ms);
+        cudaEventDestroy(last);
+        last = now;
     }
 };
 

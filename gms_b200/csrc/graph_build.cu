@@ -89,20 +89,32 @@ __global__ void k_relabel_keys(const eid_t *__restrict__ off, const vid_t *__res
     }
 }
 
-// flags[0]: malformed (offsets decrease, id outside [0,n)); flags[1]: some list is not ascending
-__global__ void k_check_csr(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, int64_t n, int *flags) {
-    int lane = threadIdx.x & 31;
-    int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t u = warp; u < n; u += nwarps) {
-        eid_t b = off[u], e = off[u + 1];
-        if (e < b) { if (lane == 0) flags[0] = 1; continue; }
-        for (eid_t s = b + lane; s < e; s += 32) {
-            vid_t v = nbr[s];
-            if (v < 0 || v >= n) flags[0] = 1;
-            if (s > b && nbr[s - 1] > v) flags[1] = 1;
-        }
+// Validation of an untrusted CSR in two streaming passes (offsets first: the slot pass trusts them).
+// Per vertex: offsets monotone and inside [0, slots] (flags[0] otherwise); counts the descents nbr[b-1] > nbr[b] that
+// sit on the first slot b of a non-empty list — those are legitimate.
+__global__ void k_check_offsets(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, int64_t n, int64_t slots,
+                                int *__restrict__ flags, unsigned long long *__restrict__ boundary_descents) {
+    unsigned long long c = 0;
+    for (int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; u < n; u += (int64_t)gridDim.x * blockDim.x) {
+        const eid_t b = off[u], e = off[u + 1];
+        if (b < 0 || e < b || e > slots) { flags[0] = 1; continue; }
+        if (e > b && b > 0 && nbr[b - 1] > nbr[b]) ++c;
     }
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(boundary_descents, c);
+}
+// Per slot: id inside [0, n) (flags[0] otherwise); counts every descent nbr[s-1] > nbr[s].  Some list is unsorted
+// exactly when there are more descents than list boundaries that explain them.
+__global__ void k_check_slots(const vid_t *__restrict__ nbr, int64_t slots, int64_t n, int *__restrict__ flags,
+                              unsigned long long *__restrict__ descents) {
+    unsigned long long c = 0;
+    for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < slots; s += (int64_t)gridDim.x * blockDim.x) {
+        const vid_t v = nbr[s];
+        if (v < 0 || v >= n) flags[0] = 1;
+        if (s > 0 && nbr[s - 1] > v) ++c;
+    }
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(descents, c);
 }
 // (u << 32 | v) for every slot: a radix sort of these keys sorts each list and keeps the lists in place
 __global__ void k_slot_keys(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, int64_t n,
@@ -147,13 +159,17 @@ Graph *graph_from_csr_device(int64_t n, const eid_t *off, const vid_t *nbr, bool
         // SortedSet's constructor sorts what it is given (sorted_set.h:64-66, so FromCGraph accepts any list order);
         // here one streaming pass checks monotone offsets, id range and order, and only an unsorted CSR pays for a sort.
         if (last && n) {
-            DevBuf<int> flags(2);
-            flags.zero();
-            k_check_csr<<<grid_for(n * 32, 256), 256, 0, r.stream>>>(g->off.p, g->nbr.p, n, flags.p); launched();
-            int h[2];
-            flags.download(h, 2);
-            GMSB_REQUIRE(h[0] == 0, "graph_from_csr: offsets not monotone or neighbour id out of range");
-            if (h[1]) {
+            DevBuf<int> flags(1);
+            DevBuf<unsigned long long> desc(2);
+            flags.zero(); desc.zero();
+            k_check_offsets<<<grid_for(n, 256), 256, 0, r.stream>>>(g->off.p, g->nbr.p, n, last, flags.p, desc.p);
+            launched();
+            GMSB_REQUIRE(flags.get(0) == 0, "graph_from_csr: offsets not monotone or outside the neighbour array");
+            k_check_slots<<<grid_for(last, 256), 256, 0, r.stream>>>(g->nbr.p, last, n, flags.p, desc.p + 1); launched();
+            unsigned long long h[2];
+            desc.download(h, 2);
+            GMSB_REQUIRE(flags.get(0) == 0, "graph_from_csr: neighbour id out of range");
+            if (h[1] > h[0]) {
                 DevBuf<uint64_t> keys(last), alt(last);
                 k_slot_keys<<<grid_for(n * 32, 256), 256, 0, r.stream>>>(g->off.p, g->nbr.p, n, keys.p); launched();
                 uint64_t *sorted = radix_sort_keys(keys.p, alt.p, last, 0, 32 + bits_for((uint64_t)(n - 1)));

@@ -581,11 +581,13 @@ uint64_t count_on_dag(int64_t n, int64_t m, const eid_t *off, const vid_t *nbr, 
             // GMSB_KCLIQUE_TRACE=1: device time of every class launch on stderr (profiling aid)
             const bool trace = std::getenv("GMSB_KCLIQUE_TRACE") != nullptr;
             cudaEvent_t ev[6] = {};
+            unsigned long long seen[6] = {};
             int nev = 0;
             auto mark = [&]() {
                 if (!trace) return;
                 cudaEventCreate(&ev[nev]);
-                cudaEventRecord(ev[nev++], r.stream);
+                cudaEventRecord(ev[nev], r.stream);
+                seen[nev++] = total.get(0);          // synchronises: per-class counts for the trace
             };
             mark();
             // The five class kernels are independent (own ticket, atomics on one total).  Each goes to its own stream
@@ -668,8 +670,8 @@ uint64_t count_on_dag(int64_t n, int64_t m, const eid_t *off, const vid_t *nbr, 
                 for (int i = 0; i + 1 < nev; ++i) {
                     float ms = 0;
                     cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
-                    std::fprintf(stderr, "[gmsb kclique k=%d] %-13s vertices=%lld ms=%.3f\n", k, names[i],
-                                 (long long)counts[i], ms);
+                    std::fprintf(stderr, "[gmsb kclique k=%d] %-13s vertices=%lld ms=%.3f cliques=%llu\n", k, names[i],
+                                 (long long)counts[i], ms, seen[i + 1] - seen[i]);
                 }
                 for (int i = 0; i < nev; ++i) cudaEventDestroy(ev[i]);
             }

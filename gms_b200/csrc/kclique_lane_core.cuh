@@ -184,6 +184,95 @@ GMSB_HD u64 lane_run_task(const u64 *cm, int pitch, int need, unsigned task, int
     return total;
 }
 
+// ---- flat form of the lane search ----------------------------------------------------------------------------------
+// lane_run_task alternates between the tree walk (lane_advance) and the leaf pass (leaf_pairs), and the lanes of a
+// warp are at different points of that alternation almost all the time: ncu showed 12 of 32 lanes active per
+// instruction (round 1).  The flat form makes ONE leaf operation the unit of every loop iteration:
+//     job  = (A, I): count sum over x in I of |A ∩ row(x)|        (I = A, or A ∩ residue class for a need == 3 task)
+//     step = take the next x of I, AND its row with A, popcount    (identical instruction sequence on every lane)
+// and moves everything else — walking the tree to the next job, pulling the next task — into flat_refill, which the
+// warp runs only when enough lanes have run dry (kclique_lane.cuh: lane_tasks_flat), so that its cost is shared.
+// All NW words of a row are visited (rows only have members after x, the lower words AND to zero): the flat form is
+// used on compact matrices of <= 4 words per row, where skipping them saves less than the divergence costs.
+template <int NW>
+struct FlatState {
+    LaneState<NW> dfs;    // the walk above the jobs (need >= 4); level -1 = no task in progress
+    u64 A[NW];            // the job's set
+    u64 imask;            // I = A & imask
+    u64 bits;             // members of I still to do in word w1
+    int w1;               // current word of I; NW = no job
+    bool exhausted;       // the task ticket has run out for this lane
+};
+
+template <int NW>
+GMSB_HD void flat_init(FlatState<NW> &s) {
+    s.dfs.level = -1;
+    s.bits = 0;
+    s.w1 = NW;
+    s.exhausted = false;
+}
+// moves to the next non-empty word of I; afterwards the job has a member to do iff s.w1 < NW
+template <int NW>
+GMSB_HD void flat_skip(FlatState<NW> &s) {
+    while (s.bits == 0 && s.w1 < NW) {
+        ++s.w1;
+#pragma unroll
+        for (int w = 1; w < NW; ++w)
+            if (w == s.w1) s.bits = s.A[w] & s.imask;
+    }
+}
+// one leaf operation (the caller checked s.w1 < NW after flat_skip)
+template <int NW>
+GMSB_HD unsigned flat_step(FlatState<NW> &s, const u64 *cm, int pitch) {
+    const int x = (s.w1 << 6) + ctz64(s.bits);
+    s.bits &= s.bits - 1;
+    const u64 *row = cm + (size_t)x * pitch;
+    unsigned cnt = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) cnt += (unsigned)popc64(s.A[w] & row[w]);
+    return cnt;
+}
+GMSB_HD unsigned flat_fetch(unsigned *counter) {
+#if defined(__CUDA_ARCH__)
+    return atomicAdd(counter, 1u);
+#else
+    return (*counter)++;
+#endif
+}
+// Gives a dry lane its next job: continues the lane's tree walk, or pulls tasks [0, t_end) from *counter until one
+// yields a job.  Task t = (first member t >> split_log2 — alist[t >> split_log2] when a list is given —, residue
+// class of the second member).  Sets s.exhausted when there is nothing left.
+template <int NW>
+GMSB_HD void flat_refill(FlatState<NW> &s, const u64 *cm, int pitch, int need, int split_log2, unsigned t_end,
+                         unsigned *counter, const unsigned short *alist) {
+    for (;;) {
+        if (s.dfs.level >= 0 && lane_advance<NW>(s.dfs, cm, pitch, need, s.A)) {
+            s.imask = ~0ull;
+            s.w1 = 0;
+            s.bits = s.A[0];
+            return;
+        }
+        const unsigned t = flat_fetch(counter);
+        if (t >= t_end) { s.exhausted = true; return; }
+        const unsigned m = t >> split_log2;
+        lane_begin<NW>(s.dfs, cm, pitch, alist ? (int)alist[m] : (int)m, (int)(t & ((1u << split_log2) - 1u)),
+                       split_log2);
+        if (need == 3) {               // the task is one job: second member in the residue class, third anywhere
+#pragma unroll
+            for (int w = 0; w < NW; ++w) s.A[w] = s.dfs.cur[w];
+            s.imask = s.dfs.stripe;
+            s.dfs.level = -1;
+            s.w1 = 0;
+            s.bits = s.A[0] & s.imask;
+            return;
+        }
+    }
+}
+// refill policy: the dry lanes are served when they are a quarter of the lanes that still have work, or nobody has a job
+GMSB_HD bool flat_should_refill(int dry_lanes, int live_lanes) {
+    return dry_lanes > 0 && (live_lanes == 0 || 4 * dry_lanes >= dry_lanes + live_lanes);
+}
+
 // ---- compaction of a candidate set of a big matrix into a compact matrix -------------------------------------------
 // set: P1 words over the positions of the big matrix; prefix[w] = members in words < w
 GMSB_HD int compact_index(const u64 *set, const int *prefix, int p) {

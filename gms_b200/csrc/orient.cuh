@@ -12,17 +12,19 @@ struct Dag {
     int64_t n = 0;
     int64_t m = 0;               // oriented edges
     int max_dplus = 0;
+    int64_t max_deg = 0;         // largest degree of the undirected graph
     DevBuf<vid_t> order;         // rank -> original id
     DevBuf<vid_t> rank;          // original id -> rank
     DevBuf<eid_t> off;           // n+1
     DevBuf<vid_t> nbr;           // m, ascending within each list, all entries > owner
+    DevBuf<int32_t> dplus;       // n: d+(v) as a compact array (random reads of it stay inside the L2)
     TcPlan *plan = nullptr;      // cached schedule for the triangle kernels
     ~Dag();
 };
 
-void degree_order(const Graph &g, DevBuf<vid_t> &order, DevBuf<vid_t> &rank);
+void degree_order(const Graph &g, DevBuf<vid_t> &order, DevBuf<vid_t> &rank, int64_t *max_deg = nullptr);
 void orient_by_rank(const Graph &g, const vid_t *rank_dev, DevBuf<eid_t> &doff, DevBuf<vid_t> &dnbr, int64_t *m_out,
-                    int *max_dplus);
+                    int *max_dplus, DevBuf<int32_t> *dplus = nullptr);
 Dag *build_degree_dag(const Graph &g);
 Graph *induce_directed(const Graph &g, const vid_t *ranking_host);
 

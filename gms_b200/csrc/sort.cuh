@@ -41,6 +41,23 @@ inline void radix_sort_pairs(uint32_t *keys, uint32_t *keys_alt, uint64_t *vals,
     *vals_out = dv.Current();
 }
 
+// Stable sort of (key32, value32) pairs on key bits [0, end_bit); returns the buffer holding the sorted values
+// (vals or vals_alt).
+inline int32_t *radix_sort_pairs32(uint32_t *keys, uint32_t *keys_alt, int32_t *vals, int32_t *vals_alt, int64_t n,
+                                   int end_bit) {
+    cub::DoubleBuffer<uint32_t> dk(keys, keys_alt);
+    cub::DoubleBuffer<int32_t> dv(vals, vals_alt);
+    size_t bytes = 0;
+    cudaStream_t s = rt().stream;
+    end_bit = end_bit > 32 ? 32 : end_bit;
+    GMSB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, dk, dv, n, 0, end_bit, s));
+    DevBuf<uint8_t> tmp(bytes);
+    GMSB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, dk, dv, n, 0, end_bit, s));
+    rt().launches += (uint64_t)((end_bit + 7) / 8 + 1);
+    GMSB_CUDA(cudaStreamSynchronize(s));
+    return dv.Current();
+}
+
 template <typename In, typename Out>
 inline void exclusive_sum(const In *in, Out *out, int64_t n) {
     size_t bytes = 0;

@@ -21,6 +21,8 @@
 #include "orient.cuh"
 #include "isect.cuh"
 #include "tc_plan.cuh"
+#include <cooperative_groups.h>
+#include <cstdlib>
 
 namespace gmsb {
 
@@ -29,59 +31,57 @@ void delete_plan(TcPlan *p) { delete p; }
 namespace {
 
 // ---- plan construction -----------------------------------------------------------------------------------------
-// One warp per vertex u: a descriptor for every out-edge; edges that cannot close a triangle (empty suffix or
-// sink v) get the sentinel key n<<2 and sort to the tail.
-__global__ void k_emit_desc(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, int64_t n,
-                            uint32_t *__restrict__ keys, uint64_t *__restrict__ vals,
-                            unsigned long long *__restrict__ work /* n: wedges arriving at v */,
-                            unsigned long long *__restrict__ vbytes /* n: algorithmic bytes arriving at v */,
-                            unsigned long long *__restrict__ acc /* [0]=B_TC [1]=wedges [2]=kept [3]=kept bytes */) {
-    int lane = threadIdx.x & 31;
-    int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    unsigned long long bytes = 0, wedges = 0, kept = 0, kbytes = 0;
-    for (int64_t u = warp; u < n; u += nwarps) {
-        eid_t b = off[u], e = off[u + 1];
-        for (eid_t s = b + lane; s < e; s += 32) {
-            vid_t v = nbr[s];
-            eid_t dv = off[v + 1] - off[v];
-            eid_t len = e - s - 1;
-            unsigned long long eb = 4ull * (unsigned long long)((e - b) + dv);
-            bytes += eb;
-            bool kp = len > 0 && dv > 0;
-            uint32_t cls = len <= kShortLen ? 0u : (len <= kMidLen ? 1u : 2u);
-            keys[s] = kp ? (((uint32_t)v << kClassBits) | cls) : ((uint32_t)n << kClassBits);
-            vals[s] = ((uint64_t)(s + 1) << kLenBits) | (uint64_t)len;
-            if (kp) {
-                atomicAdd(&work[v], (unsigned long long)len);
-                atomicAdd(&vbytes[v], eb);
-                wedges += len; kept++; kbytes += eb;
+// The schedule groups the suffix descriptors of all oriented edges (u,v) by their closing vertex v and, inside v,
+// by length class.  It is a counting sort keyed on (v, class) — the transposed (in-edge) index of the DAG — built in
+// two streaming passes over the oriented CSR instead of a radix sort of |E+| (key, descriptor) pairs:
+//   pass 1  k_plan_count    one RED per edge into the 64-bit counter of (v, class): descriptors << 38 | suffix lengths
+//           k_classify      per vertex: hub or light, number of CTA items (cost-balanced), segment sizes
+//           two scans       item numbers and descriptor segments of the hubs
+//           k_plan_layout   per vertex: the counters become absolute write cursors (or a LIGHT / DEAD mark), items written
+//   pass 2  k_plan_scatter  one ATOM per edge takes the descriptor's slot in v's segment; edges into light vertices are
+//                           appended to the merge / gallop lists instead (warp-aggregated cursors)
+// Round 1 emitted 251 M (key, descriptor) pairs at scale 24 and radix-sorted them (4 onesweep passes over 12 B per
+// pair + 2 x 251 M 64-bit atomics for the per-vertex work) and then flagged / scanned / compacted the light edges.
+constexpr int kCntShift = 38;                                  // counter word = (descriptors << 38) | sum of lengths
+constexpr unsigned long long kWorkMask = (1ull << kCntShift) - 1ull;
+constexpr unsigned long long kPosLight = 1ull << 63;           // cursor marks: edges into a light vertex ...
+constexpr unsigned long long kPosDead = 1ull << 62;            // ... and into a vertex that closes no triangle
+
+__device__ __forceinline__ uint32_t len_class(eid_t len) { return len <= kShortLen ? 0u : (len <= kMidLen ? 1u : 2u); }
+
+template <int G>
+__global__ void __launch_bounds__(256)
+k_plan_count(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, const int32_t *__restrict__ dplus,
+             int64_t n, unsigned long long *__restrict__ cw /* 3n */,
+             unsigned long long *__restrict__ acc /* [0]=sum d+(u)+d+(v), all edges  [1]=wedges  [2]=kept edges
+                                                     [3]=sum d+(u), kept edges */) {
+    const int sub = threadIdx.x % G;
+    const int64_t grp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / G;
+    const int64_t ngrp = ((int64_t)gridDim.x * blockDim.x) / G;
+    unsigned long long deg2 = 0, wedges = 0, kept = 0, ku = 0;
+    for (int64_t u = grp; u < n; u += ngrp) {
+        const eid_t b = off[u], e = off[u + 1];
+        const unsigned long long du = (unsigned long long)(e - b);
+        for (eid_t s = b + sub; s < e; s += G) {
+            const vid_t v = nbr[s];
+            const int dv = dplus[v];
+            const eid_t len = e - s - 1;
+            deg2 += du + (unsigned long long)dv;
+            if (len > 0 && dv > 0) {
+                atomicAdd(&cw[3 * (int64_t)v + len_class(len)], (1ull << kCntShift) | (unsigned long long)len);
+                wedges += (unsigned long long)len; kept++; ku += du;
             }
         }
     }
     for (int o = 16; o; o >>= 1) {
-        bytes += __shfl_xor_sync(0xffffffffu, bytes, o);
+        deg2 += __shfl_xor_sync(0xffffffffu, deg2, o);
         wedges += __shfl_xor_sync(0xffffffffu, wedges, o);
         kept += __shfl_xor_sync(0xffffffffu, kept, o);
-        kbytes += __shfl_xor_sync(0xffffffffu, kbytes, o);
+        ku += __shfl_xor_sync(0xffffffffu, ku, o);
     }
-    if (lane == 0 && (bytes | kept)) {
-        atomicAdd(&acc[0], bytes); atomicAdd(&acc[1], wedges); atomicAdd(&acc[2], kept); atomicAdd(&acc[3], kbytes);
+    if ((threadIdx.x & 31) == 0 && deg2) {
+        atomicAdd(&acc[0], deg2); atomicAdd(&acc[1], wedges); atomicAdd(&acc[2], kept); atomicAdd(&acc[3], ku);
     }
-}
-
-__device__ __forceinline__ int64_t first_key_ge(const uint32_t *__restrict__ keys, int64_t lo, int64_t hi, uint32_t x) {
-    while (lo < hi) {
-        int64_t mid = (lo + hi) >> 1;
-        if (keys[mid] < x) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
-
-// inoff[v] = first descriptor of vertex v (keys sorted ascending, length cnt); inoff[n] = cnt
-__global__ void k_vertex_bounds(const uint32_t *__restrict__ keys, int64_t cnt, int64_t n, int64_t *__restrict__ inoff) {
-    for (int64_t x = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; x <= n; x += (int64_t)gridDim.x * blockDim.x)
-        inoff[x] = first_key_ge(keys, 0, cnt, (uint32_t)x << kClassBits);
 }
 
 struct PlanParams {
@@ -93,62 +93,137 @@ struct PlanParams {
 
 // Per vertex: hub or not, and into how many CTA items its descriptor group is cut.
 __global__ void k_classify(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, int64_t n,
-                           const int64_t *__restrict__ inoff, const unsigned long long *__restrict__ work,
-                           const unsigned long long *__restrict__ vbytes,
-                           unsigned long long *__restrict__ cls /* [0]=bitmap bytes [1]=bitmap wedges */,
-                           PlanParams pp, int64_t *__restrict__ nitems /* n+1, exclusive-scanned later */,
-                           int *__restrict__ max_span_words) {
-    int mx = 0;
-    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x) {
-        int64_t cnt = inoff[v + 1] - inoff[v];
-        int64_t k = 0;
-        if (cnt > 0 && (pp.variant == GMSB_TC_AUTO || pp.variant == GMSB_TC_BITMAP)) {
-            eid_t ob = off[v], oe = off[v + 1];
-            int64_t span = (int64_t)nbr[oe - 1] - v;            // bit x = w - v - 1, x in [0, span)
-            bool hub = span <= pp.hub_bits &&
-                       (pp.variant == GMSB_TC_BITMAP || (long long)work[v] >= pp.hub_min_work);
-            if (hub) {
-                int64_t words = (span + 31) >> 5;
-                long long setup = 16ll * (oe - ob);
-                long long target = pp.item_cost > setup ? pp.item_cost : setup;
-                long long cost = (long long)work[v] + 4ll * cnt;
-                k = (cost + target - 1) / target;
-                if (k < 1) k = 1;
-                if (k > cnt) k = cnt;
-                mx = max(mx, (int)words);
-                atomicAdd(&cls[0], vbytes[v]);
-                atomicAdd(&cls[1], work[v]);
+                           const unsigned long long *__restrict__ cw, PlanParams pp,
+                           int64_t *__restrict__ nitems /* n+1 */, int64_t *__restrict__ seg /* n+1 */,
+                           unsigned long long *__restrict__ cls /* [0]=hub edges [1]=hub wedges [2]=sum cnt*d+(v), hubs
+                                                                  [3]=sum cnt*d+(v), all  [4]=light edges */,
+                           int *__restrict__ mx /* [0]=max span words [1]=max d+ of a hub */) {
+    int mxw = 0, mxd = 0;
+    unsigned long long he = 0, hw = 0, hb = 0, ab = 0, le = 0;
+    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v <= n; v += (int64_t)gridDim.x * blockDim.x) {
+        int64_t k = 0, sg = 0;
+        if (v < n) {
+            const unsigned long long w0 = cw[3 * v], w1 = cw[3 * v + 1], w2 = cw[3 * v + 2];
+            const int64_t cnt = (int64_t)((w0 >> kCntShift) + (w1 >> kCntShift) + (w2 >> kCntShift));
+            if (cnt > 0) {
+                const long long work = (long long)((w0 & kWorkMask) + (w1 & kWorkMask) + (w2 & kWorkMask));
+                const eid_t ob = off[v], oe = off[v + 1];
+                const unsigned long long dv = (unsigned long long)(oe - ob);
+                ab += (unsigned long long)cnt * dv;
+                bool hub = false;
+                if (pp.variant == GMSB_TC_AUTO || pp.variant == GMSB_TC_BITMAP) {
+                    const int64_t span = (int64_t)nbr[oe - 1] - v;          // bit x = w - v - 1, x in [0, span)
+                    hub = span <= pp.hub_bits && (pp.variant == GMSB_TC_BITMAP || work >= pp.hub_min_work);
+                    if (hub) {
+                        const long long setup = 16ll * (long long)dv;
+                        const long long target = pp.item_cost > setup ? pp.item_cost : setup;
+                        const long long cost = work + 4ll * cnt;
+                        k = (cost + target - 1) / target;
+                        if (k < 1) k = 1;
+                        if (k > cnt) k = cnt;
+                        const int64_t chunk = (cnt + k - 1) / k;
+                        k = (cnt + chunk - 1) / chunk;                      // no empty trailing items
+                        sg = cnt;
+                        mxw = max(mxw, (int)((span + 31) >> 5));
+                        mxd = max(mxd, (int)dv);
+                        he += (unsigned long long)cnt; hw += (unsigned long long)work; hb += (unsigned long long)cnt * dv;
+                    }
+                }
+                if (!hub) le += (unsigned long long)cnt;
             }
         }
         nitems[v] = k;
+        seg[v] = sg;
     }
-    for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if ((threadIdx.x & 31) == 0 && mx) atomicMax(max_span_words, mx);
+    for (int o = 16; o; o >>= 1) {
+        mxw = max(mxw, __shfl_xor_sync(0xffffffffu, mxw, o));
+        mxd = max(mxd, __shfl_xor_sync(0xffffffffu, mxd, o));
+        he += __shfl_xor_sync(0xffffffffu, he, o); hw += __shfl_xor_sync(0xffffffffu, hw, o);
+        hb += __shfl_xor_sync(0xffffffffu, hb, o); ab += __shfl_xor_sync(0xffffffffu, ab, o);
+        le += __shfl_xor_sync(0xffffffffu, le, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (mxw) { atomicMax(&mx[0], mxw); atomicMax(&mx[1], mxd); }
+        if (he) { atomicAdd(&cls[0], he); atomicAdd(&cls[1], hw); atomicAdd(&cls[2], hb); }
+        if (ab) atomicAdd(&cls[3], ab);
+        if (le) atomicAdd(&cls[4], le);
+    }
 }
 
-__global__ void k_fill_items(int64_t n, const uint32_t *__restrict__ keys, const int64_t *__restrict__ inoff,
-                             const int64_t *__restrict__ nitems, const int64_t *__restrict__ item_base,
-                             Item *__restrict__ items) {
+// Counters -> write cursors; items of the hubs (a slice of the descriptor segment each, with its class boundaries).
+__global__ void k_plan_layout(int64_t n, unsigned long long *__restrict__ cw, const int64_t *__restrict__ nitems,
+                              const int64_t *__restrict__ item_base, const int64_t *__restrict__ segbase,
+                              Item *__restrict__ items) {
     for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x) {
-        int64_t k = nitems[v];
-        if (!k) continue;
-        int64_t b = inoff[v], e = inoff[v + 1], cnt = e - b;
-        int64_t c0 = first_key_ge(keys, b, e, ((uint32_t)v << kClassBits) | 1u);     // end of class 0
-        int64_t c1 = first_key_ge(keys, c0, e, ((uint32_t)v << kClassBits) | 2u);    // end of class 1
-        int64_t chunk = (cnt + k - 1) / k;
-        int64_t w = item_base[v];
+        const int64_t c0 = (int64_t)(cw[3 * v] >> kCntShift), c1 = (int64_t)(cw[3 * v + 1] >> kCntShift),
+                      c2 = (int64_t)(cw[3 * v + 2] >> kCntShift);
+        const int64_t cnt = c0 + c1 + c2, k = nitems[v];
+        if (cnt == 0) { cw[3 * v] = kPosDead; cw[3 * v + 1] = kPosDead; cw[3 * v + 2] = kPosDead; continue; }
+        if (k == 0) { cw[3 * v] = kPosLight; cw[3 * v + 1] = kPosLight; cw[3 * v + 2] = kPosLight; continue; }
+        const int64_t b = segbase[v];
+        cw[3 * v] = (unsigned long long)b;
+        cw[3 * v + 1] = (unsigned long long)(b + c0);
+        cw[3 * v + 2] = (unsigned long long)(b + c0 + c1);
+        const int64_t chunk = (cnt + k - 1) / k, w = item_base[v];
         for (int64_t j = 0; j < k; ++j) {
-            int64_t s = b + j * chunk;
-            int64_t c = e - s < chunk ? e - s : chunk;
-            if (c < 0) c = 0;
+            const int64_t s = j * chunk;                           // first descriptor of the slice, relative to b
+            const int64_t c = cnt - s < chunk ? cnt - s : chunk;
             Item it;
-            it.v = (int32_t)v; it.begin = s; it.count = (int32_t)c;
-            int64_t a0 = c0 - s, a1 = c1 - s;
+            it.v = (int32_t)v; it.begin = b + s; it.count = (int32_t)c;
+            const int64_t a0 = c0 - s, a1 = c0 + c1 - s;
             it.n0 = (int32_t)(a0 < 0 ? 0 : (a0 > c ? c : a0));
             it.n1 = (int32_t)(a1 < 0 ? 0 : (a1 > c ? c : a1));
             items[w + j] = it;
         }
     }
+}
+
+template <int G>
+__global__ void __launch_bounds__(256)
+k_plan_scatter(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, const int32_t *__restrict__ dplus,
+               int64_t n, unsigned long long *__restrict__ pos /* 3n */, uint64_t *__restrict__ desc, int variant,
+               int ratio, uint64_t *__restrict__ m_desc, vid_t *__restrict__ m_v, uint64_t *__restrict__ g_desc,
+               vid_t *__restrict__ g_v, unsigned long long *__restrict__ cursors /* [0]=merge [1]=gallop */,
+               unsigned long long *__restrict__ acc /* [0] = sum of d+(u) over hub edges */) {
+    namespace cg = cooperative_groups;
+    const int sub = threadIdx.x % G;
+    const int64_t grp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / G;
+    const int64_t ngrp = ((int64_t)gridDim.x * blockDim.x) / G;
+    unsigned long long hub_u = 0;
+    for (int64_t u = grp; u < n; u += ngrp) {
+        const eid_t b = off[u], e = off[u + 1];
+        for (eid_t s = b + sub; s < e; s += G) {
+            const eid_t len = e - s - 1;
+            if (len <= 0) continue;
+            const vid_t v = nbr[s];
+            const unsigned long long old = atomicAdd(&pos[3 * (int64_t)v + len_class(len)], 1ull);
+            if (old & kPosDead) continue;
+            const uint64_t ds = ((uint64_t)(s + 1) << kLenBits) | (uint64_t)len;
+            if (!(old & kPosLight)) {
+                desc[old] = ds;
+                hub_u += (unsigned long long)(e - b);
+                continue;
+            }
+            const long long a = (long long)len, dv = dplus[v];
+            const long long lo = a < dv ? a : dv, hi = a < dv ? dv : a;
+            const bool gallop = variant == GMSB_TC_GALLOP || (variant != GMSB_TC_MERGE && hi >= (long long)ratio * lo);
+            if (gallop) {
+                cg::coalesced_group act = cg::coalesced_threads();
+                unsigned long long base = 0;
+                if (act.thread_rank() == 0) base = atomicAdd(&cursors[1], (unsigned long long)act.size());
+                const unsigned long long i = act.shfl(base, 0) + act.thread_rank();
+                g_desc[i] = ds; g_v[i] = v;
+            } else {
+                cg::coalesced_group act = cg::coalesced_threads();
+                unsigned long long base = 0;
+                if (act.thread_rank() == 0) base = atomicAdd(&cursors[0], (unsigned long long)act.size());
+                const unsigned long long i = act.shfl(base, 0) + act.thread_rank();
+                m_desc[i] = ds; m_v[i] = v;
+            }
+        }
+    }
+    for (int o = 16; o; o >>= 1) hub_u += __shfl_xor_sync(0xffffffffu, hub_u, o);
+    if ((threadIdx.x & 31) == 0 && hub_u) atomicAdd(&acc[0], hub_u);
 }
 
 // Order key of an item: L2 tile of its first suffix (tile-major order keeps the lists that concurrently running
@@ -167,31 +242,6 @@ __global__ void k_item_keys(const Item *__restrict__ items, int64_t cnt, const u
         if (!wide) { atomicAdd(n_small, 1ull); atomicMax(small_words, words); }
         keys[i] = ((uint64_t)wide << 63) | (tile << 32) | (uint64_t)(uint32_t)(n - 1 - it.v);
     }
-}
-
-// Light descriptors: flag for merge / gallop by the length ratio of suffix and N+(v).
-__global__ void k_flag_light(const uint32_t *__restrict__ keys, const uint64_t *__restrict__ vals, int64_t cnt,
-                             const eid_t *__restrict__ off, const int64_t *__restrict__ nitems, int variant,
-                             int ratio, uint8_t *__restrict__ fm, uint8_t *__restrict__ fg) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < cnt; i += (int64_t)gridDim.x * blockDim.x) {
-        uint32_t v = keys[i] >> kClassBits;
-        bool light = nitems[v] == 0;
-        bool gallop = false;
-        if (light) {
-            long long a = (long long)(vals[i] & kLenMask), b = off[v + 1] - off[v];
-            long long lo = a < b ? a : b, hi = a < b ? b : a;
-            gallop = variant == GMSB_TC_GALLOP || (variant != GMSB_TC_MERGE && hi >= (long long)ratio * lo);
-        }
-        fm[i] = light && !gallop;
-        fg[i] = light && gallop;
-    }
-}
-
-__global__ void k_compact_light(const uint32_t *__restrict__ keys, const uint64_t *__restrict__ vals, int64_t cnt,
-                                const uint8_t *__restrict__ flag, const int64_t *__restrict__ pos,
-                                uint64_t *__restrict__ odesc, vid_t *__restrict__ ov) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < cnt; i += (int64_t)gridDim.x * blockDim.x)
-        if (flag[i]) { odesc[pos[i]] = vals[i]; ov[pos[i]] = (vid_t)(keys[i] >> kClassBits); }
 }
 
 // ---- counting kernels ----------------------------------------------------------------------------------------------
@@ -376,50 +426,67 @@ TcPlan *build_plan(const Dag &d, const gmsb_tc_options &opt) {
         const int64_t n = d.n, m = d.m;
         GMSB_REQUIRE(d.max_dplus < (1 << kLenBits), "tc: out-degree too large for the descriptor format");
         GMSB_REQUIRE(m < (int64_t(1) << (64 - kLenBits)), "tc: too many edges for the descriptor format");
-        GMSB_REQUIRE(n < (int64_t(1) << (32 - kClassBits)), "tc: too many vertices for the 32-bit schedule key");
+        // the per-(vertex, class) counter packs (descriptors << 38 | sum of suffix lengths)
+        GMSB_REQUIRE(d.max_deg < (int64_t(1) << (64 - kCntShift - 1)) &&
+                         (double)d.max_deg * (double)d.max_dplus < (double)(1ull << kCntShift),
+                     "tc: in-degree x out-degree too large for the schedule counters");
         size_t smem_cap = r.smem_optin ? r.smem_optin : 48 * 1024;
         int hub_bits = opt.hub_bitmap_bits;
         if ((size_t)hub_bits / 8 > smem_cap - 1024) hub_bits = (int)((smem_cap - 1024) * 8);
         if (m == 0 || n == 0) return p;
+        PhaseTrace tr("GMSB_TC_TRACE");
 
-        p->keys_a.alloc(m); p->keys_b.alloc(m); p->vals_a.alloc(m); p->vals_b.alloc(m);
-        DevBuf<unsigned long long> work(n), vbytes(n), acc(4), cls(2);
-        work.zero(); vbytes.zero(); acc.zero(); cls.zero();
-        k_emit_desc<<<grid_for(n * 32, 256), 256, 0, r.stream>>>(d.off.p, d.nbr.p, n, p->keys_a.p, p->vals_a.p,
-                                                                 work.p, vbytes.p, acc.p);
+        constexpr int G = 8;                    // lanes per vertex in the two edge passes (mean d+ is ~16, median far less)
+        DevBuf<unsigned long long> cw(3 * (size_t)n), acc(4), cls(5);
+        DevBuf<int> mx(2);
+        cw.zero(); acc.zero(); cls.zero(); mx.zero();
+        k_plan_count<G><<<grid_for(n * G, 256), 256, 0, r.stream>>>(d.off.p, d.nbr.p, d.dplus.p, n, cw.p, acc.p);
         launched();
-        radix_sort_pairs(p->keys_a.p, p->keys_b.p, p->vals_a.p, p->vals_b.p, m, bits_for((uint64_t)n) + kClassBits,
-                         &p->sorted_keys, &p->sorted_vals);
-        unsigned long long h_acc[4];
-        acc.download(h_acc, 4);
-        p->algorithmic_bytes = h_acc[0];
-        p->wedges = h_acc[1];
-        p->n_desc = (int64_t)h_acc[2];
-        p->bytes_kept = h_acc[3];
-        const int64_t cnt = p->n_desc;
-        if (cnt == 0) return p;
-
-        DevBuf<int64_t> inoff(n + 1), nitems(n + 1), item_base(n + 1);
-        k_vertex_bounds<<<grid_for(n + 1, 256), 256, 0, r.stream>>>(p->sorted_keys, cnt, n, inoff.p); launched();
-        DevBuf<int> mxw(1);
-        mxw.zero(); nitems.zero();
+        tr.mark("plan: count pass");
+        DevBuf<int64_t> nitems(n + 1), seg(n + 1), item_base(n + 1), segbase(n + 1);
         PlanParams pp{opt.variant, hub_bits, (long long)opt.hub_min_work,
                       opt.reserved[0] > 0 ? (long long)opt.reserved[0] : 262144ll};
-        k_classify<<<grid_for(n, 256), 256, 0, r.stream>>>(d.off.p, d.nbr.p, n, inoff.p, work.p, vbytes.p, cls.p, pp,
-                                                          nitems.p, mxw.p);
+        k_classify<<<grid_for(n + 1, 256), 256, 0, r.stream>>>(d.off.p, d.nbr.p, n, cw.p, pp, nitems.p, seg.p, cls.p,
+                                                              mx.p);
         launched();
         exclusive_sum(nitems.p, item_base.p, n + 1);
-        p->n_items = item_base.get(n);
-        p->max_span_words = mxw.get(0);
-        unsigned long long h_cls[2];
-        cls.download(h_cls, 2);
-        p->bytes_bitmap = h_cls[0];
+        exclusive_sum(seg.p, segbase.p, n + 1);
+        unsigned long long h_acc[4], h_cls[5];
+        int h_mx[2];
+        acc.download(h_acc, 4);
+        cls.download(h_cls, 5);
+        mx.download(h_mx, 2);
+        p->algorithmic_bytes = 4ull * h_acc[0];
+        p->wedges = h_acc[1];
+        p->n_desc = (int64_t)h_acc[2];
+        p->bytes_kept = 4ull * (h_acc[3] + h_cls[3]);
+        p->n_bitmap_edges = (int64_t)h_cls[0];
         p->wedges_bitmap = h_cls[1];
+        p->max_span_words = h_mx[0];
+        p->max_hub_dplus = h_mx[1];
+        const int64_t n_light = (int64_t)h_cls[4];
+        tr.mark("plan: classify + scans");
+        if (p->n_desc == 0) return p;
+        p->n_items = item_base.get(n);
+        p->items.alloc(p->n_items);
+        p->desc.alloc(p->n_bitmap_edges);
+        k_plan_layout<<<grid_for(n, 256), 256, 0, r.stream>>>(n, cw.p, nitems.p, item_base.p, segbase.p, p->items.p);
+        launched();
+        // both light lists are sized for all light edges; the scatter pass decides merge / gallop per edge
+        p->m_desc.alloc(n_light); p->m_v.alloc(n_light); p->g_desc.alloc(n_light); p->g_v.alloc(n_light);
+        DevBuf<unsigned long long> cursors(2), hub_u(1);
+        cursors.zero(); hub_u.zero();
+        k_plan_scatter<G><<<grid_for(n * G, 256), 256, 0, r.stream>>>(
+            d.off.p, d.nbr.p, d.dplus.p, n, cw.p, p->desc.p, opt.variant, opt.gallop_ratio, p->m_desc.p, p->m_v.p,
+            p->g_desc.p, p->g_v.p, cursors.p, hub_u.p);
+        launched();
+        unsigned long long h_cur[2];
+        cursors.download(h_cur, 2);
+        p->n_merge = (int64_t)h_cur[0];
+        p->n_gallop = (int64_t)h_cur[1];
+        p->bytes_bitmap = 4ull * (hub_u.get(0) + h_cls[2]);
+        tr.mark("plan: layout + scatter pass");
         if (p->n_items) {
-            p->items.alloc(p->n_items);
-            k_fill_items<<<grid_for(n, 256), 256, 0, r.stream>>>(n, p->sorted_keys, inoff.p, nitems.p, item_base.p,
-                                                                p->items.p);
-            launched();
             // order: tile-major, heaviest first inside a tile
             DevBuf<uint64_t> ik(p->n_items), ik2(p->n_items);
             DevBuf<Item> items2(p->n_items);
@@ -427,7 +494,7 @@ TcPlan *build_plan(const Dag &d, const gmsb_tc_options &opt) {
             DevBuf<unsigned long long> nsm(1);
             DevBuf<int> smw(1);
             nsm.zero(); smw.zero();
-            k_item_keys<<<grid_for(p->n_items, 256), 256, 0, r.stream>>>(p->items.p, p->n_items, p->sorted_vals, n,
+            k_item_keys<<<grid_for(p->n_items, 256), 256, 0, r.stream>>>(p->items.p, p->n_items, p->desc.p, n,
                                                                         tile_shift, d.off.p, d.nbr.p, ik.p, nsm.p, smw.p);
             launched();
             p->n_items_small = (int64_t)nsm.get(0);
@@ -442,33 +509,8 @@ TcPlan *build_plan(const Dag &d, const gmsb_tc_options &opt) {
             GMSB_CUDA(cudaStreamSynchronize(r.stream));
             p->items = std::move(items2);
         }
-        // light edges -> two compacted lists
-        DevBuf<uint8_t> fm(cnt), fg(cnt);
-        DevBuf<int64_t> pm(cnt + 1), pg(cnt + 1);
-        k_flag_light<<<grid_for(cnt, 256), 256, 0, r.stream>>>(p->sorted_keys, p->sorted_vals, cnt, d.off.p, nitems.p,
-                                                              opt.variant, opt.gallop_ratio, fm.p, fg.p);
-        launched();
-        exclusive_sum(fm.p, pm.p, cnt);
-        exclusive_sum(fg.p, pg.p, cnt);
-        p->n_merge = pm.get(cnt - 1) + fm.get(cnt - 1);
-        p->n_gallop = pg.get(cnt - 1) + fg.get(cnt - 1);
-        p->n_bitmap_edges = cnt - p->n_merge - p->n_gallop;
-        if (p->n_merge) {
-            p->m_desc.alloc(p->n_merge); p->m_v.alloc(p->n_merge);
-            k_compact_light<<<grid_for(cnt, 256), 256, 0, r.stream>>>(p->sorted_keys, p->sorted_vals, cnt, fm.p, pm.p,
-                                                                     p->m_desc.p, p->m_v.p);
-            launched();
-        }
-        if (p->n_gallop) {
-            p->g_desc.alloc(p->n_gallop); p->g_v.alloc(p->n_gallop);
-            k_compact_light<<<grid_for(cnt, 256), 256, 0, r.stream>>>(p->sorted_keys, p->sorted_vals, cnt, fg.p, pg.p,
-                                                                     p->g_desc.p, p->g_v.p);
-            launched();
-        }
-        // the key halves are no longer needed once the lists are built
-        p->keys_a.release(); p->keys_b.release();
-        if (p->sorted_vals == p->vals_a.p) p->vals_b.release(); else p->vals_a.release();
         GMSB_CUDA(cudaStreamSynchronize(r.stream));
+        tr.mark("plan: item order");
     } catch (...) { delete p; throw; }
     return p;
 }
@@ -528,7 +570,7 @@ void tc_total(Graph &g, const gmsb_tc_options &opt_in, uint64_t *out, gmsb_tc_st
             GMSB_REQUIRE(resident >= 1, "tc: bitmap kernel does not fit on an SM");
             const int grid = (int)std::min<int64_t>(mine, (int64_t)r.sm_count * resident);
             kern<<<grid, BLOCK, smem, r.stream>>>(items, pi, P, mine, (uint32_t)cap_words, d.off.p, d.nbr.p,
-                                                  p.sorted_vals, total.p, ticket);
+                                                  p.desc.p, total.p, ticket);
             launched();
         };
         const int shape = opt.reserved[2];              // experiments: one launch with another CTA shape

@@ -1,5 +1,7 @@
 // tc_plan.cuh — the triangle schedule ("plan") shared by the counting kernels (tc.cu) and the per-edge support
 // kernels (tc_support.cu): suffix descriptors grouped by their closing vertex v, hub items, light-edge lists.
+// The grouping is a counting sort keyed on (v, length class): one pass counts, a scan lays the segments out, a second
+// pass scatters every descriptor to its segment through an atomic cursor (tc.cu: build_plan).
 #pragma once
 #include "common.cuh"
 #include "orient.cuh"
@@ -39,11 +41,10 @@ struct TcPlan {
     uint64_t algorithmic_bytes = 0;     // B_TC over ALL oriented edges
     uint64_t wedges = 0;
     uint64_t bytes_bitmap = 0, bytes_kept = 0, wedges_bitmap = 0;
-    // backing stores of the sorted arrays (double buffers keep the result in either half)
-    DevBuf<uint32_t> keys_a, keys_b;
-    DevBuf<uint64_t> vals_a, vals_b;
-    uint32_t *sorted_keys = nullptr;
-    uint64_t *sorted_vals = nullptr;    // descriptors grouped by v (ascending), class, then u
+    int max_hub_dplus = 0;              // largest d+ among hub vertices (tc_support sizes its shared lists with it)
+    // hub descriptors grouped by v (ascending), then length class; the order inside a class is the order in which the
+    // scatter pass reached the edges (roughly ascending u)
+    DevBuf<uint64_t> desc;
 };
 
 // Builds (or reuses) the degree-oriented DAG and the schedule cached on the graph handle.

@@ -213,7 +213,7 @@ void tc_support(Graph &g, DevBuf<uint32_t> &sup) {
     if (p.n_items) {
         constexpr int BLOCK = 512;
         auto kern = k_support_bitmap<BLOCK>;
-        const size_t smem = ((size_t)p.max_span_words + 1 + 2 * (size_t)d.max_dplus) * 4;
+        const size_t smem = ((size_t)p.max_span_words + 1 + 2 * (size_t)p.max_hub_dplus) * 4;   // only hubs are staged
         GMSB_REQUIRE(smem <= r.smem_optin, "tc_support: neighbourhood too large for shared memory");
         if (smem > 48 * 1024)
             GMSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -223,8 +223,8 @@ void tc_support(Graph &g, DevBuf<uint32_t> &sup) {
         const int grid = (int)std::min<int64_t>(p.n_items, (int64_t)r.sm_count * resident);
         DevBuf<unsigned int> ticket(1);
         ticket.zero();
-        kern<<<grid, BLOCK, smem, r.stream>>>(p.items.p, p.n_items, (uint32_t)p.max_span_words, d.max_dplus, d.off.p,
-                                              d.nbr.p, p.sorted_vals, sup.p, ticket.p);
+        kern<<<grid, BLOCK, smem, r.stream>>>(p.items.p, p.n_items, (uint32_t)p.max_span_words, p.max_hub_dplus, d.off.p,
+                                              d.nbr.p, p.desc.p, sup.p, ticket.p);
         launched();
     }
     if (p.n_merge) {

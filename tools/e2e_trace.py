@@ -1,0 +1,48 @@
+"""Phase breakdown of the end-to-end path (host CSR -> HBM -> ranking -> DAG -> schedule -> count) at one scale:
+
+    GMSB_TC_TRACE=1 python tools/e2e_trace.py [--scale 24] [--reps 3]
+
+The library prints the device time of every phase of the representation build on stderr; this script adds the wall
+time of the two C-ABI calls (gmsb_graph_from_csr from pinned host memory, gmsb_tc_total_ex with nothing cached)."""
+import argparse
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402  (pinned host memory)
+import gms_b200 as G  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--scale", type=int, default=24)
+    ap.add_argument("--reps", type=int, default=3)
+    args = ap.parse_args()
+    G.set_device(0)
+    src, dst = G.generate_rmat(args.scale)
+    g = G.Graph.from_edgelist(src, dst, True)
+    del src, dst
+    n, slots = g.n, g.slots
+    off_h = torch.empty(n + 1, dtype=torch.int64).pin_memory()
+    nbr_h = torch.empty(max(slots, 1), dtype=torch.int32).pin_memory()
+    G.capi._check(G.lib().gmsb_graph_export_csr(g.h, off_h.numpy(), nbr_h.numpy()))
+    g.free()
+    for rep in range(args.reps):
+        print(f"--- rep {rep}", file=sys.stderr, flush=True)
+        t0 = time.perf_counter()
+        gg = G.Graph.from_csr(off_h.numpy(), nbr_h.numpy()[:slots])
+        t1 = time.perf_counter()
+        c, st = gg.tc_total_ex(reuse_plan=False)
+        t2 = time.perf_counter()
+        gg.free()
+        print(json.dumps({"scale": args.scale, "rep": rep, "from_csr_ms": round((t1 - t0) * 1e3, 2),
+                          "tc_total_ms": round((t2 - t1) * 1e3, 2), "triangles": c,
+                          "ms_orient": round(st["ms_orient"], 2), "ms_count": round(st["ms_count"], 2),
+                          "ms_bitmap": round(st["ms_bitmap"], 2), "n_items": st["bitmap_items"],
+                          "edges": [st["edges_bitmap"], st["edges_merge"], st["edges_gallop"]]}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
