@@ -319,7 +319,7 @@ def run_ours(args):
 
     def e2e_step():
         if sharded is None:
-            gg = G.Graph.from_csr(off_h.numpy(), nbr_h.numpy()[:slots])
+            gg = G.Graph.from_csr(off_h.numpy(), nbr_h.numpy()[:slots], orient=True)   # GMSB_BUILD_ORIENT
         else:
             off_d, nbr_d = sharded.upload()
             gg = G.Graph.from_csr_device(n, off_d.data_ptr(), nbr_d.data_ptr())

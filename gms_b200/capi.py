@@ -59,6 +59,7 @@ SIGNATURES = {
     "gmsb_generate_rmat": (C.c_int, [C.c_int, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_int, _i32p, _i32p]),
     "gmsb_generate_uniform": (C.c_int, [C.c_int, C.c_int64, _i32p, _i32p]),
     "gmsb_graph_from_csr": (C.c_int, [C.c_int64, _i64p, _i32p, C.c_int, C.POINTER(C.c_void_p)]),
+    "gmsb_graph_from_csr_ex": (C.c_int, [C.c_int64, _i64p, _i32p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "gmsb_graph_from_csr_device": (C.c_int, [C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     "gmsb_graph_from_edgelist": (C.c_int, [C.c_int64, _i32p, _i32p, C.c_int, C.POINTER(C.c_void_p)]),
     "gmsb_graph_from_edgelist_device": (C.c_int, [C.c_int64, C.c_void_p, C.c_void_p, C.c_int,
@@ -82,6 +83,23 @@ SIGNATURES = {
     "gmsb_difference_batch": (C.c_int, [C.c_void_p, C.c_int64, _i32p, _i32p, _i64p, C.c_void_p, C.c_int64]),
     "gmsb_union_batch": (C.c_int, [C.c_void_p, C.c_int64, _i32p, _i32p, _i64p, C.c_void_p, C.c_int64]),
     "gmsb_union_count_batch": (C.c_int, [C.c_void_p, C.c_int64, _i32p, _i32p, _u64p]),
+    "gmsb_set_from_host": (C.c_int, [_i32p, C.c_int64, C.POINTER(C.c_void_p)]),
+    "gmsb_set_range": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p)]),
+    "gmsb_set_neighbourhood": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]),
+    "gmsb_set_clone": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "gmsb_set_free": (C.c_int, [C.c_void_p]),
+    "gmsb_set_cardinality": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "gmsb_set_to_host": (C.c_int, [C.c_void_p, _i32p]),
+    "gmsb_set_contains": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int)]),
+    "gmsb_set_add": (C.c_int, [C.c_void_p, C.c_int32]),
+    "gmsb_set_remove": (C.c_int, [C.c_void_p, C.c_int32]),
+    "gmsb_set_equal": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
+    "gmsb_set_op": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "gmsb_set_op_inplace": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p]),
+    "gmsb_set_op_count": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]),
+    "gmsb_set_op_count_many": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_void_p), _u64p]),
+    "gmsb_set_op_many": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "gmsb_set_op_count_neighbourhoods": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, _u64p]),
     "gmsb_pair_similarity": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, _i32p, _i32p, _f64p]),
     "gmsb_edge_similarity": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int64)]),
     "gmsb_kclique_count": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]),
@@ -164,12 +182,16 @@ class Graph:
 
     # --- construction
     @staticmethod
-    def from_csr(offsets, nbrs, directed=False):
+    def from_csr(offsets, nbrs, directed=False, orient=False):
+        """orient=True: GMSB_BUILD_ORIENT — the degree-oriented representation is built while the arrays upload."""
         offsets = np.ascontiguousarray(offsets, np.int64)
         n = len(offsets) - 1
         nn = len(nbrs)
         h = C.c_void_p()
-        _check(lib().gmsb_graph_from_csr(n, offsets, _ids(nbrs), int(directed), C.byref(h)))
+        if orient:
+            _check(lib().gmsb_graph_from_csr_ex(n, offsets, _ids(nbrs), int(directed), 1, C.byref(h)))
+        else:
+            _check(lib().gmsb_graph_from_csr(n, offsets, _ids(nbrs), int(directed), C.byref(h)))
         assert nn >= offsets[-1]
         return Graph(h)
 
@@ -333,3 +355,99 @@ class Graph:
         out = C.c_uint64(0)
         _check(lib().gmsb_kclique_count_ordered(self.h, k, C.byref(out)))
         return out.value
+
+
+SET_OPS = {"intersect": 0, "union": 1, "difference": 2}
+
+
+class DeviceSet:
+    """Device-resident sorted set (gmsb_set_*): the reference's Set concept (sorted_set.h) with results kept in HBM."""
+
+    def __init__(self, elems=(), _h=None):
+        if _h is not None:
+            self.h = _h
+            return
+        h = C.c_void_p()
+        arr = np.ascontiguousarray(elems, np.int32)
+        _check(lib().gmsb_set_from_host(_ids(arr), len(arr), C.byref(h)))
+        self.h = h
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().gmsb_set_free(self.h)
+            self.h = None
+
+    @staticmethod
+    def range(bound):
+        h = C.c_void_p()
+        _check(lib().gmsb_set_range(bound, C.byref(h)))
+        return DeviceSet(_h=h)
+
+    @staticmethod
+    def neighbourhood(graph, v):
+        h = C.c_void_p()
+        _check(lib().gmsb_set_neighbourhood(graph.h, v, C.byref(h)))
+        s = DeviceSet(_h=h)
+        s._graph = graph                      # the view borrows the graph's CSR
+        return s
+
+    def clone(self):
+        h = C.c_void_p()
+        _check(lib().gmsb_set_clone(self.h, C.byref(h)))
+        return DeviceSet(_h=h)
+
+    def cardinality(self):
+        n = C.c_int64(0)
+        _check(lib().gmsb_set_cardinality(self.h, C.byref(n)))
+        return n.value
+
+    def to_array(self):
+        out = np.zeros(max(self.cardinality(), 1), np.int32)
+        _check(lib().gmsb_set_to_host(self.h, out))
+        return out[:self.cardinality()]
+
+    def contains(self, x):
+        f = C.c_int(0)
+        _check(lib().gmsb_set_contains(self.h, x, C.byref(f)))
+        return bool(f.value)
+
+    def add(self, x):
+        _check(lib().gmsb_set_add(self.h, x))
+
+    def remove(self, x):
+        _check(lib().gmsb_set_remove(self.h, x))
+
+    def __eq__(self, other):
+        f = C.c_int(0)
+        _check(lib().gmsb_set_equal(self.h, other.h, C.byref(f)))
+        return bool(f.value)
+
+    def op(self, kind, other):
+        h = C.c_void_p()
+        _check(lib().gmsb_set_op(SET_OPS[kind], self.h, other.h, C.byref(h)))
+        return DeviceSet(_h=h)
+
+    def op_inplace(self, kind, other):
+        _check(lib().gmsb_set_op_inplace(SET_OPS[kind], self.h, other.h))
+
+    def op_count(self, kind, other):
+        out = C.c_uint64(0)
+        _check(lib().gmsb_set_op_count(SET_OPS[kind], self.h, other.h, C.byref(out)))
+        return out.value
+
+    def op_count_many(self, kind, others):
+        hs = (C.c_void_p * max(len(others), 1))(*[o.h for o in others])
+        out = np.zeros(max(len(others), 1), np.uint64)
+        _check(lib().gmsb_set_op_count_many(SET_OPS[kind], self.h, len(others), hs, out))
+        return out[:len(others)]
+
+    def op_many(self, kind, others):
+        hs = (C.c_void_p * max(len(others), 1))(*[o.h for o in others])
+        outs = (C.c_void_p * max(len(others), 1))()
+        _check(lib().gmsb_set_op_many(SET_OPS[kind], self.h, len(others), hs, outs))
+        return [DeviceSet(_h=C.c_void_p(outs[i])) for i in range(len(others))]
+
+    def op_count_neighbourhoods(self, kind, graph, members):
+        out = np.zeros(max(members.cardinality(), 1), np.uint64)
+        _check(lib().gmsb_set_op_count_neighbourhoods(SET_OPS[kind], self.h, graph.h, members.h, out))
+        return out[:members.cardinality()]

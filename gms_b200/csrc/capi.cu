@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include "orient.cuh"
 #include "ops.cuh"
+#include "sets.cuh"
 
 #include <algorithm>
 #include <cstring>
@@ -183,6 +184,17 @@ GMSB_API int gmsb_graph_from_csr(int64_t n, const int64_t *off, const int32_t *n
         *out = reinterpret_cast<gmsb_graph_t>(graph_from_csr_device(n, off, nbr, directed != 0, true));
     });
 }
+GMSB_API int gmsb_graph_from_csr_ex(int64_t n, const int64_t *off, const int32_t *nbr, int directed, int flags,
+                                    gmsb_graph_t *out) {
+    return guarded([&] {
+        GMSB_REQUIRE(out, "null output handle");
+        GMSB_REQUIRE((flags & ~GMSB_BUILD_ORIENT) == 0, "graph_from_csr_ex: unknown flag");
+        if ((flags & GMSB_BUILD_ORIENT) && !directed)
+            *out = reinterpret_cast<gmsb_graph_t>(graph_from_csr_host_pipelined(n, off, nbr));
+        else
+            *out = reinterpret_cast<gmsb_graph_t>(graph_from_csr_device(n, off, nbr, directed != 0, true));
+    });
+}
 GMSB_API int gmsb_graph_from_csr_device(int64_t n, const int64_t *off, const int32_t *nbr, int directed, gmsb_graph_t *out) {
     return guarded([&] {
         GMSB_REQUIRE(out, "null output handle");
@@ -356,6 +368,90 @@ GMSB_API int gmsb_edge_similarity(gmsb_graph_t g, int metric, double *out, int64
     return guarded([&] {
         GMSB_REQUIRE(metric >= 0 && metric <= GMSB_SIM_PREF_ATT, "invalid similarity measure");
         edge_similarity(G(g), metric, out, m_out);
+    });
+}
+
+// ---- device-resident sets -------------------------------------------------------------------------------------------------
+namespace {
+inline DevSet &S(gmsb_set_t h) {
+    GMSB_REQUIRE(h != nullptr, "null set handle");
+    return *reinterpret_cast<DevSet *>(h);
+}
+inline void check_op(int op) { GMSB_REQUIRE(op >= GMSB_SET_INTERSECT && op <= GMSB_SET_DIFFERENCE, "unknown set operation"); }
+}  // namespace
+GMSB_API int gmsb_set_from_host(const int32_t *elems, int64_t count, gmsb_set_t *out) {
+    return guarded([&] { GMSB_REQUIRE(out, "null output handle"); rt(); *out = reinterpret_cast<gmsb_set_t>(set_from_host(elems, count)); });
+}
+GMSB_API int gmsb_set_range(int64_t bound, gmsb_set_t *out) {
+    return guarded([&] { GMSB_REQUIRE(out, "null output handle"); *out = reinterpret_cast<gmsb_set_t>(set_range(bound)); });
+}
+GMSB_API int gmsb_set_neighbourhood(gmsb_graph_t g, int32_t v, gmsb_set_t *out) {
+    return guarded([&] { GMSB_REQUIRE(out, "null output handle"); *out = reinterpret_cast<gmsb_set_t>(set_neighbourhood(G(g), v)); });
+}
+GMSB_API int gmsb_set_clone(gmsb_set_t a, gmsb_set_t *out) {
+    return guarded([&] { GMSB_REQUIRE(out, "null output handle"); *out = reinterpret_cast<gmsb_set_t>(set_clone(S(a))); });
+}
+GMSB_API int gmsb_set_free(gmsb_set_t a) { return guarded([&] { delete reinterpret_cast<DevSet *>(a); }); }
+GMSB_API int gmsb_set_cardinality(gmsb_set_t a, int64_t *n) {
+    return guarded([&] { GMSB_REQUIRE(n, "null argument"); *n = S(a).n; });
+}
+GMSB_API int gmsb_set_to_host(gmsb_set_t a, int32_t *out) { return guarded([&] { set_to_host(S(a), out); }); }
+GMSB_API int gmsb_set_contains(gmsb_set_t a, int32_t x, int *flag) {
+    return guarded([&] { GMSB_REQUIRE(flag, "null argument"); *flag = set_contains(S(a), x) ? 1 : 0; });
+}
+GMSB_API int gmsb_set_add(gmsb_set_t a, int32_t x) { return guarded([&] { set_add(S(a), x); }); }
+GMSB_API int gmsb_set_remove(gmsb_set_t a, int32_t x) { return guarded([&] { set_remove(S(a), x); }); }
+GMSB_API int gmsb_set_equal(gmsb_set_t a, gmsb_set_t b, int *flag) {
+    return guarded([&] { GMSB_REQUIRE(flag, "null argument"); *flag = set_equal(S(a), S(b)) ? 1 : 0; });
+}
+GMSB_API int gmsb_set_op(int op, gmsb_set_t a, gmsb_set_t b, gmsb_set_t *out) {
+    return guarded([&] {
+        GMSB_REQUIRE(out, "null output handle");
+        check_op(op);
+        DevSet *bs[1] = {&S(b)}, *res[1] = {nullptr};
+        set_op_many(op, S(a), 1, bs, res);
+        *out = reinterpret_cast<gmsb_set_t>(res[0]);
+    });
+}
+GMSB_API int gmsb_set_op_inplace(int op, gmsb_set_t a, gmsb_set_t b) {
+    return guarded([&] {
+        check_op(op);
+        DevSet *bs[1] = {&S(b)}, *res[1] = {nullptr};
+        set_op_many(op, S(a), 1, bs, res);
+        DevSet &dst = S(a);
+        dst.own = std::move(res[0]->own);
+        dst.p = dst.own.p;
+        dst.n = res[0]->n;
+        delete res[0];
+    });
+}
+GMSB_API int gmsb_set_op_count(int op, gmsb_set_t a, gmsb_set_t b, uint64_t *out) {
+    return guarded([&] {
+        GMSB_REQUIRE(out, "null output");
+        check_op(op);
+        DevSet *bs[1] = {&S(b)};
+        set_op_count_many(op, S(a), 1, bs, out);
+    });
+}
+GMSB_API int gmsb_set_op_count_many(int op, gmsb_set_t a, int64_t count, const gmsb_set_t *bs, uint64_t *out) {
+    return guarded([&] {
+        GMSB_REQUIRE(count >= 0 && (count == 0 || (bs && out)), "set_op_count_many: bad arguments");
+        check_op(op);
+        set_op_count_many(op, S(a), count, reinterpret_cast<DevSet *const *>(bs), out);
+    });
+}
+GMSB_API int gmsb_set_op_many(int op, gmsb_set_t a, int64_t count, const gmsb_set_t *bs, gmsb_set_t *outs) {
+    return guarded([&] {
+        GMSB_REQUIRE(count >= 0 && (count == 0 || (bs && outs)), "set_op_many: bad arguments");
+        check_op(op);
+        set_op_many(op, S(a), count, reinterpret_cast<DevSet *const *>(bs), reinterpret_cast<DevSet **>(outs));
+    });
+}
+GMSB_API int gmsb_set_op_count_neighbourhoods(int op, gmsb_set_t a, gmsb_graph_t g, gmsb_set_t members, uint64_t *out) {
+    return guarded([&] {
+        check_op(op);
+        GMSB_REQUIRE(out || S(members).n == 0, "null output");
+        set_op_count_members(op, S(a), G(g), S(members), out);
     });
 }
 

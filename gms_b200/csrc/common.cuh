@@ -150,6 +150,7 @@ struct Graph {
     DevBuf<eid_t> off;          // n+1
     DevBuf<vid_t> nbr;          // slots, ascending within each list
     Dag *dag = nullptr;         // cached degree-oriented DAG (undirected graphs only)
+    bool dag_pinned = false;    // the DAG was built with the graph (GMSB_BUILD_ORIENT): reuse_plan = 0 keeps it
     ~Graph();
 };
 

@@ -12,6 +12,8 @@
 #include "common.cuh"
 #include "sort.cuh"
 #include "isect.cuh"
+#include "orient.cuh"
+#include <vector>
 
 namespace gmsb {
 
@@ -103,12 +105,20 @@ __global__ void k_check_offsets(const eid_t *__restrict__ off, const vid_t *__re
     for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(boundary_descents, c);
 }
+// offsets only (the upload pipeline validates them before the neighbour slots have arrived)
+__global__ void k_check_offsets_only(const eid_t *__restrict__ off, int64_t n, int64_t slots, int *__restrict__ flags) {
+    for (int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; u < n; u += (int64_t)gridDim.x * blockDim.x) {
+        const eid_t b = off[u], e = off[u + 1];
+        if (b < 0 || e < b || e > slots) flags[0] = 1;
+    }
+}
 // Per slot: id inside [0, n) (flags[0] otherwise); counts every descent nbr[s-1] > nbr[s].  Some list is unsorted
 // exactly when there are more descents than list boundaries that explain them.
-__global__ void k_check_slots(const vid_t *__restrict__ nbr, int64_t slots, int64_t n, int *__restrict__ flags,
-                              unsigned long long *__restrict__ descents) {
+__global__ void k_check_slots(const vid_t *__restrict__ nbr, int64_t first, int64_t slots, int64_t n,
+                              int *__restrict__ flags, unsigned long long *__restrict__ descents) {
     unsigned long long c = 0;
-    for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < slots; s += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t s = first + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < slots;
+         s += (int64_t)gridDim.x * blockDim.x) {
         const vid_t v = nbr[s];
         if (v < 0 || v >= n) flags[0] = 1;
         if (s > 0 && nbr[s - 1] > v) ++c;
@@ -165,7 +175,7 @@ Graph *graph_from_csr_device(int64_t n, const eid_t *off, const vid_t *nbr, bool
             k_check_offsets<<<grid_for(n, 256), 256, 0, r.stream>>>(g->off.p, g->nbr.p, n, last, flags.p, desc.p);
             launched();
             GMSB_REQUIRE(flags.get(0) == 0, "graph_from_csr: offsets not monotone or outside the neighbour array");
-            k_check_slots<<<grid_for(last, 256), 256, 0, r.stream>>>(g->nbr.p, last, n, flags.p, desc.p + 1); launched();
+            k_check_slots<<<grid_for(last, 256), 256, 0, r.stream>>>(g->nbr.p, 0, last, n, flags.p, desc.p + 1); launched();
             unsigned long long h[2];
             desc.download(h, 2);
             GMSB_REQUIRE(flags.get(0) == 0, "graph_from_csr: neighbour id out of range");
@@ -178,6 +188,111 @@ Graph *graph_from_csr_device(int64_t n, const eid_t *off, const vid_t *nbr, bool
         }
         GMSB_CUDA(cudaStreamSynchronize(r.stream));
     } catch (...) { delete g; throw; }
+    return g;
+}
+
+// gmsb_graph_from_csr_ex(GMSB_BUILD_ORIENT): the host CSR is uploaded in chunks on a copy stream while the library
+// stream already works on what has arrived — the degree ranking needs the offsets only (the first 6 % of the bytes),
+// the validation and the relabel + count pass of the orientation run per vertex range as soon as that range's
+// neighbour slots are on the device.  When the last chunk lands only the emit + sort passes are left.  (Host memory
+// should be pinned; with pageable memory the copies are staged by the driver and overlap less.)
+Graph *graph_from_csr_host_pipelined(int64_t n, const eid_t *off, const vid_t *nbr) {
+    GMSB_REQUIRE(n >= 0 && off != nullptr, "graph_from_csr: bad arguments");
+    Runtime &r = rt();
+    const eid_t last = off[n];
+    GMSB_REQUIRE(off[0] == 0 && last >= 0, "graph_from_csr: offsets must start at 0 and be non-negative");
+    GMSB_REQUIRE(last == 0 || nbr != nullptr, "graph_from_csr: null neighbour array");
+    if (n == 0 || last == 0) return graph_from_csr_device(n, off, nbr, false, true);
+    struct Streams {
+        cudaStream_t copy = nullptr;
+        std::vector<cudaEvent_t> ev;
+        ~Streams() {
+            for (auto e : ev) cudaEventDestroy(e);
+            if (copy) cudaStreamDestroy(copy);
+        }
+    } st;
+    auto *g = new Graph();
+    OrientPipeline pipe;
+    try {
+        g->n = n; g->slots = last; g->directed = false;
+        g->off.alloc(n + 1);
+        g->nbr.alloc(last);
+        GMSB_CUDA(cudaStreamCreateWithFlags(&st.copy, cudaStreamNonBlocking));
+        // allocations above may have been served from blocks whose last use is still queued on the library stream
+        GMSB_CUDA(cudaStreamSynchronize(r.stream));
+        auto mark = [&]() {
+            cudaEvent_t e;
+            GMSB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            st.ev.push_back(e);
+            GMSB_CUDA(cudaEventRecord(e, st.copy));
+            return e;
+        };
+        GMSB_CUDA(cudaMemcpyAsync(g->off.p, off, sizeof(eid_t) * (n + 1), cudaMemcpyHostToDevice, st.copy));
+        cudaEvent_t ev_off = mark();
+        // vertex ranges of about equal slot counts (the host array is only used to pick the cuts: a malformed one is
+        // caught by the device check of the offsets below before any range is processed)
+        constexpr int kChunks = 16;
+        std::vector<int64_t> cut(1, 0);
+        for (int c = 1; c < kChunks; ++c) {
+            const eid_t target = last / kChunks * c;
+            int64_t lo = cut.back(), hi = n;
+            while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (off[mid] < target) lo = mid + 1; else hi = mid; }
+            cut.push_back(lo);
+        }
+        cut.push_back(n);
+        std::vector<cudaEvent_t> ev_chunk;
+        eid_t sent = 0;
+        for (int c = 0; c < kChunks; ++c) {
+            eid_t upto = c + 1 == kChunks ? last : off[cut[c + 1]];
+            if (upto < sent || upto > last) upto = sent;                    // malformed offsets: rejected below
+            if (upto > sent)
+                GMSB_CUDA(cudaMemcpyAsync(g->nbr.p + sent, nbr + sent, sizeof(vid_t) * (size_t)(upto - sent),
+                                          cudaMemcpyHostToDevice, st.copy));
+            sent = upto;
+            ev_chunk.push_back(mark());
+        }
+        // library stream: offsets -> validation -> ranking; then range by range
+        DevBuf<int> flags(1);
+        DevBuf<unsigned long long> desc(2);
+        flags.zero(); desc.zero();
+        GMSB_CUDA(cudaStreamWaitEvent(r.stream, ev_off, 0));
+        k_check_offsets_only<<<grid_for(n, 256), 256, 0, r.stream>>>(g->off.p, n, last, flags.p); launched();
+        GMSB_REQUIRE(flags.get(0) == 0, "graph_from_csr: offsets not monotone or outside the neighbour array");
+        orient_pipeline_begin(*g, pipe);
+        eid_t checked = 0;
+        for (int c = 0; c < kChunks; ++c) {
+            GMSB_CUDA(cudaStreamWaitEvent(r.stream, ev_chunk[c], 0));
+            const eid_t upto = c + 1 == kChunks ? last : off[cut[c + 1]];
+            if (upto > checked) {
+                k_check_slots<<<grid_for(upto - checked, 256), 256, 0, r.stream>>>(g->nbr.p, checked, upto, n, flags.p,
+                                                                                  desc.p + 1);
+                launched();
+                checked = upto;
+            }
+            orient_pipeline_range(*g, pipe, cut[c], cut[c + 1]);
+        }
+        k_check_offsets<<<grid_for(n, 256), 256, 0, r.stream>>>(g->off.p, g->nbr.p, n, last, flags.p, desc.p); launched();
+        unsigned long long h[2];
+        desc.download(h, 2);
+        GMSB_REQUIRE(flags.get(0) == 0, "graph_from_csr: neighbour id out of range");
+        orient_pipeline_finish(*g, pipe);
+        g->dag = pipe.d;
+        pipe.d = nullptr;
+        g->dag_pinned = true;
+        if (h[1] > h[0]) {          // some list was not ascending: sort the lists (the DAG does not depend on their order)
+            DevBuf<uint64_t> keys(last), alt(last);
+            k_slot_keys<<<grid_for(n * 32, 256), 256, 0, r.stream>>>(g->off.p, g->nbr.p, n, keys.p); launched();
+            uint64_t *sorted = radix_sort_keys(keys.p, alt.p, last, 0, 32 + bits_for((uint64_t)(n - 1)));
+            k_low32<<<grid_for(last, 256), 256, 0, r.stream>>>(sorted, last, g->nbr.p); launched();
+        }
+        GMSB_CUDA(cudaStreamSynchronize(r.stream));
+    } catch (...) {
+        cudaStreamSynchronize(st.copy);
+        cudaStreamSynchronize(r.stream);
+        delete pipe.d;
+        delete g;
+        throw;
+    }
     return g;
 }
 

@@ -30,6 +30,8 @@
 #include "kclique_lane.cuh"
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <vector>
 
 namespace gmsb {
 
@@ -477,11 +479,19 @@ __global__ void k_class_counts(const vid_t *__restrict__ verts, int64_t cnt, con
     }
 }
 
+__global__ void k_list_degrees(const vid_t *__restrict__ verts, int64_t cnt, const eid_t *__restrict__ off,
+                               int *__restrict__ deg) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < cnt; i += (int64_t)gridDim.x * blockDim.x) {
+        const vid_t u = verts[i];
+        deg[i] = (int)(off[u + 1] - off[u]);
+    }
+}
+
 // Which kernels run the d+ > 32 sub-problems: the lane-parallel ones (kclique_lane.cuh) or the warp-cooperative ones
 // above.  GMSB_KCLIQUE_IMPL=warp|lane forces one family (A/B measurements, tests); the default takes the lane
 // kernels where they are faster (measured on B200) and supported (4 <= k <= 10).
 constexpr int kLaneMinK = 5;
-constexpr int kLaneDefaultFlags = 1;
+constexpr int kPairMinDefault = 512;
 bool use_lane_kernels(int k) {
     const char *e = std::getenv("GMSB_KCLIQUE_IMPL");
     if (e && !std::strcmp(e, "warp")) return false;
@@ -574,9 +584,22 @@ uint64_t count_on_dag(int64_t n, int64_t m, const eid_t *off, const vid_t *nbr, 
             cc.download(bound, 4);
             DevBuf<unsigned int> tickets(5);
             tickets.zero();
-            // GMSB_KCLIQUE_L3=0|1: per-warp third-level matrices (kclique_lane.cuh: warp_tasks) off / on, for A/B runs
-            const char *l3 = std::getenv("GMSB_KCLIQUE_L3");
-            const int lane_flags = l3 ? (std::atoi(l3) != 0 ? 1 : 0) : kLaneDefaultFlags;
+            // A/B switches (environment): GMSB_KCLIQUE_M3NEED=4 builds a warp's third-level matrix only when at least
+            // four vertices are left to pick inside the set (default 3); GMSB_KCLIQUE_HUGE=old selects the round-1
+            // one-CTA-per-vertex-part kernel for d+ > 512 instead of the decoupled pair kernel
+            auto env_int = [](const char *name, int dflt) {
+                const char *e = std::getenv(name);
+                return e ? std::atoi(e) : dflt;
+            };
+            const int lane_flags = std::min(4, std::max(3, env_int("GMSB_KCLIQUE_M3NEED", 3))) << lane::kFlagM3NeedShift;
+            const char *huge_env = std::getenv("GMSB_KCLIQUE_HUGE");
+            // the pair kernel searches through third-level matrices, which pay when >= 5 vertices are left below (u, S[i]);
+            // GMSB_KCLIQUE_HUGE=pair forces it for smaller k (then it searches M2 directly with the flat lanes).
+            // GMSB_KCLIQUE_PAIR_MIN=512|256|128: smallest out-degree class that goes through the pair kernel.
+            const bool huge_old = huge_env ? !std::strcmp(huge_env, "old") : k < 7;
+            const int pair_min = env_int("GMSB_KCLIQUE_PAIR_MIN", kPairMinDefault);
+            const int64_t n_pair = huge_old ? 0 : (pair_min <= 128 ? bound[2] : (pair_min <= 256 ? bound[1] : bound[0]));
+            const int64_t mid_from = huge_old ? (int64_t)bound[0] : n_pair;     // first vertex left to the class kernels
             DevBuf<lane::u64> spill;
             // GMSB_KCLIQUE_TRACE=1: device time of every class launch on stderr (profiling aid)
             const bool trace = std::getenv("GMSB_KCLIQUE_TRACE") != nullptr;
@@ -613,7 +636,70 @@ uint64_t count_on_dag(int64_t n, int64_t m, const eid_t *off, const vid_t *nbr, 
                 }
             }
             int next_aux = 0;
-            if (n_huge) {           // d+ > 512: CTA-wide top of the tree, compact matrices below
+            DevBuf<int64_t> pair_base, m1_off;
+            DevBuf<lane::u64> m1;
+            if (n_pair) {
+                // d+ > 512, decoupled: M1 of every such vertex to global memory, then (vertex, member) items.
+                // Sizes come from the (few thousand) out-degrees on the host; the vertices are processed in batches
+                // whose matrices fit kM1Budget bytes.
+                std::vector<vid_t> hv((size_t)n_pair);
+                GMSB_CUDA(cudaMemcpyAsync(hv.data(), vb.p, sizeof(vid_t) * n_pair, cudaMemcpyDeviceToHost, r.stream));
+                GMSB_CUDA(cudaStreamSynchronize(r.stream));
+                std::vector<int> hd((size_t)n_pair);
+                {
+                    // out-degrees of the listed vertices (descending): two offsets each
+                    DevBuf<int> dd((size_t)n_pair);
+                    k_list_degrees<<<grid_for(n_pair, 256), 256, 0, r.stream>>>(vb.p, n_pair, off, dd.p); launched();
+                    dd.download(hd.data(), (size_t)n_pair);
+                }
+                constexpr size_t kM1Budget = size_t(12) << 30;
+                constexpr int PBLOCK = 256;
+                const size_t smem2 = lane::pair_smem_words(maxD, PBLOCK / 32) * 8;
+                GMSB_REQUIRE(smem2 + 4096 <= r.smem_optin, "kclique_count: out-degree too large for the pair kernel");
+                auto kern2 = lane::k_kclique_lane_pair<PBLOCK>;
+                GMSB_CUDA(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+                int resident2 = 0;
+                GMSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident2, kern2, PBLOCK, smem2));
+                GMSB_REQUIRE(resident2 >= 1, "kclique_count: pair kernel does not fit on an SM");
+                constexpr int BBLOCK = 256;
+                const size_t smem1 = ((size_t)(BBLOCK / 32) * lane::huge_pitch(maxD) + (size_t)((maxD + 1) >> 1)) * 8;
+                auto kern1 = lane::k_kclique_m1_build<BBLOCK>;
+                GMSB_CUDA(cudaFuncSetAttribute(kern1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+                int64_t t0 = 0;
+                int64_t item0 = 0;                       // global numbering of the items, for the multi-GPU deal
+                while (t0 < n_pair) {
+                    std::vector<int64_t> h_m1((size_t)0), h_items((size_t)0);
+                    size_t words = 0;
+                    int64_t items = 0, t1 = t0;
+                    while (t1 < n_pair) {
+                        const size_t w = (size_t)hd[t1] * (size_t)lane::huge_pitch(hd[t1]);
+                        if (t1 > t0 && (words + w) * 8 > kM1Budget) break;
+                        h_m1.push_back((int64_t)words); h_items.push_back(items);
+                        words += w; items += hd[t1]; ++t1;
+                    }
+                    h_items.push_back(items);
+                    const int64_t nv = t1 - t0;
+                    m1.alloc(words);
+                    m1_off.alloc((size_t)nv); pair_base.alloc((size_t)nv + 1);
+                    m1_off.upload(h_m1.data(), (size_t)nv);
+                    pair_base.upload(h_items.data(), (size_t)nv + 1);
+                    const int grid1 = (int)std::min<int64_t>(nv, (int64_t)r.sm_count * 4);
+                    kern1<<<grid1, BBLOCK, smem1, r.stream>>>(vb.p, t0, nv, off, nbr, m1_off.p, m1.p, maxD); launched();
+                    // this process's items of the batch: global item numbers congruent to pi modulo P
+                    const int shift = (int)(((int64_t)pi - item0 % P + P) % P);
+                    const int64_t mine = items > shift ? (items - shift + P - 1) / P : 0;
+                    if (mine) {
+                        GMSB_CUDA(cudaMemsetAsync(tickets.p, 0, sizeof(unsigned int), r.stream));
+                        const int grid2 = (int)std::min<int64_t>(mine, (int64_t)r.sm_count * resident2);
+                        kern2<<<grid2, PBLOCK, smem2, r.stream>>>(vb.p, t0, pair_base.p, nv, items, off, m1_off.p, m1.p, k,
+                                                                  maxD, total.p, tickets.p, shift, P, lane_flags);
+                        launched();
+                    }
+                    GMSB_CUDA(cudaStreamSynchronize(r.stream));      // host vectors / batch buffers are reused
+                    item0 += items;
+                    t0 = t1;
+                }
+            } else if (n_huge && huge_old) {    // round-1 kernel: CTA-wide top of the tree, compact matrices below, one CTA per SM
                 exclusive_sum(parts.p, item_base.p, n_huge + 1);
                 const int64_t n_items = item_base.get(n_huge);
                 auto launch_huge = [&](auto kern, int block) {
@@ -637,8 +723,8 @@ uint64_t count_on_dag(int64_t n, int64_t m, const eid_t *off, const vid_t *nbr, 
             // third-level boxes only where they shorten the rows: matrices of 4 or 8 words per row
             auto mid = [&](auto kern, int block, bool boxes, int64_t first, int64_t cnt, unsigned int *ticket) {
                 if (cnt <= 0) return;
-                const int flags = boxes ? lane_flags : 0;
-                const size_t dyn = (flags & 1) ? (size_t)(block / 32) * sizeof(lane::WarpBox) : 0;
+                const int flags = lane_flags;
+                const size_t dyn = boxes ? (size_t)(block / 32) * sizeof(lane::WarpBox) : 0;
                 GMSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
                 int resident = 0;
                 GMSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, block, dyn));
@@ -652,9 +738,10 @@ uint64_t count_on_dag(int64_t n, int64_t m, const eid_t *off, const vid_t *nbr, 
                 mid(kern, block, boxes, first, cnt, ticket);
                 mark();
             };
-            mid_marked(lane::k_kclique_lane_mid<8, 384, 2>, 384, true, bound[0], bound[1] - bound[0], tickets.p + 1);
-            mid_marked(lane::k_kclique_lane_mid<4, 256, 4>, 256, true, bound[1], bound[2] - bound[1], tickets.p + 2);
-            mid_marked(lane::k_kclique_lane_mid<2, 128, 8>, 128, false, bound[2], bound[3] - bound[2], tickets.p + 3);
+            auto from = [&](int64_t b) { return std::max<int64_t>(b, mid_from); };
+            mid_marked(lane::k_kclique_lane_mid<8, 384, 2>, 384, true, from(bound[0]), bound[1] - from(bound[0]), tickets.p + 1);
+            mid_marked(lane::k_kclique_lane_mid<4, 256, 4>, 256, true, from(bound[1]), bound[2] - from(bound[1]), tickets.p + 2);
+            mid_marked(lane::k_kclique_lane_mid<2, 128, 8>, 128, false, from(bound[2]), bound[3] - from(bound[2]), tickets.p + 3);
             mid_marked(lane::k_kclique_lane_mid<1, 128, 8>, 128, false, bound[3], nb - bound[3], tickets.p + 4);
             if (!trace) {
                 for (auto &st : aux) {           // join: the library stream continues after every class
@@ -693,10 +780,16 @@ __global__ void k_expand_sources(const eid_t *__restrict__ off, int64_t n, vid_t
     for (int64_t u = warp; u < n; u += nwarps)
         for (eid_t e = off[u] + lane; e < off[u + 1]; e += 32) src[e] = (vid_t)u;
 }
-__global__ void k_max_out(const eid_t *__restrict__ off, int64_t n, int *out) {
+// out[0] = largest out-degree; out[1] = 1 when some arc does not go from a lower to a higher id.  The matrix builders
+// only look for out-neighbours among the LATER members of S (ids ascend with position), which is right exactly when
+// every arc ascends — what gmsb_orient and InduceDirectedGraph produce; any other directed input is re-oriented.
+__global__ void k_max_out(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, int64_t n, int *out) {
     int mx = 0;
-    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x)
-        mx = max(mx, (int)(off[v + 1] - off[v]));
+    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x) {
+        const eid_t b = off[v], e = off[v + 1];
+        mx = max(mx, (int)(e - b));
+        if (e > b && nbr[b] <= (vid_t)v) out[1] = 1;          // lists ascend: the first entry is the smallest
+    }
     for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if ((threadIdx.x & 31) == 0) atomicMax(out, mx);
 }
@@ -713,17 +806,20 @@ void kclique_count(Graph &g, int k, uint64_t *out, int pi, int P) {
             *out = count_on_dag(g.n, g.slots, g.off.p, g.nbr.p, k, pi, P);
             return;
         }
-        DevBuf<int> mx(1);
+        DevBuf<int> mx(2);
         mx.zero();
-        k_max_out<<<grid_for(g.n, 256), 256, 0, r.stream>>>(g.off.p, g.n, mx.p); launched();
-        const int D = mx.get(0);
-        if (matrix_words(D) * 4 + 28 * 1024 <= r.smem_optin) {
+        k_max_out<<<grid_for(g.n, 256), 256, 0, r.stream>>>(g.off.p, g.nbr.p, g.n, mx.p); launched();
+        int h_mx[2];
+        mx.download(h_mx, 2);
+        const int D = h_mx[0];
+        if (h_mx[1] == 0 && matrix_words(D) * 4 + 28 * 1024 <= r.smem_optin) {
             *out = count_on_dag(g.n, g.slots, g.off.p, g.nbr.p, k, pi, P);
             return;
         }
         // The reference's own degeneracy pipeline orients from later- to earlier-removed vertices, which leaves
-        // out-degrees unbounded.  Clique counts do not depend on the orientation, so re-orient the
-        // underlying undirected graph by degree and count there.
+        // out-degrees unbounded, and a directed graph from a file or an edge list may have arcs in
+        // both id directions.  Clique counts do not depend on the orientation (KcListing accepts any DAG), so
+        // re-orient the underlying undirected graph by degree and count there.
         DevBuf<vid_t> src(g.slots);
         k_expand_sources<<<grid_for(g.n * 32, 256), 256, 0, r.stream>>>(g.off.p, g.n, src.p); launched();
         Graph *und = graph_from_edgelist_device(g.slots, src.p, g.nbr.p, true);

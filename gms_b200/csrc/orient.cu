@@ -170,14 +170,16 @@ __device__ __forceinline__ unsigned window_mask(int rel, int deg, int i0) {
 
 // (1) relabel + count: rnbr[s] = rank[nbr[s]] is stored so that the emit pass streams instead of gathering again;
 // d+(u) goes to cnt[rank[u] + 1].  Vertices with a big list are queued (bigq) for k_relabel_big.
+// (The pass runs over the vertex range [u_begin, n): the upload pipeline calls it range by range; ids are bounds-checked
+// here because in that pipeline the validation of a range is only enqueued, not yet read back, when this runs.)
 __global__ void __launch_bounds__(256)
-k_relabel_count(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, int64_t n,
+k_relabel_count(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, int64_t u_begin, int64_t n, int64_t n_all,
                 const vid_t *__restrict__ rank, vid_t *__restrict__ rnbr, eid_t *__restrict__ cnt,
                 vid_t *__restrict__ bigq, int *__restrict__ nbigq) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t u0 = warp * 32; u0 < n; u0 += nwarps * 32) {
+    for (int64_t u0 = u_begin + warp * 32; u0 < n; u0 += nwarps * 32) {
         const WarpChunk ck = load_chunk(off, u0, n, lane);
         const int64_t u = u0 + lane;
         const vid_t ru = u < n ? rank[u] : 0;
@@ -190,7 +192,11 @@ k_relabel_count(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, in
             const eid_t s = __shfl_sync(0xffffffffu, ck.abs, owner) + (i - __shfl_sync(0xffffffffu, ck.rel, owner));
             const vid_t ro = __shfl_sync(0xffffffffu, ru, owner);
             vid_t rv = -1;
-            if (act) { rv = rank[nbr[s]]; rnbr[s] = rv; }
+            if (act) {
+                const vid_t v = nbr[s];
+                rv = (uint64_t)v < (uint64_t)n_all ? rank[v] : -1;
+                rnbr[s] = rv;
+            }
             const unsigned kept = __ballot_sync(0xffffffffu, act && rv > ro);
             c += __popc(kept & window_mask(ck.rel, ck.deg, i0));
         }
@@ -203,13 +209,14 @@ k_relabel_count(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, in
 // big lists: blockIdx.x = queue entry, blockIdx.y = one of gridDim.y interleaved parts of the list
 __global__ void __launch_bounds__(256)
 k_relabel_big(const vid_t *__restrict__ bigq, const eid_t *__restrict__ off, const vid_t *__restrict__ nbr,
-              const vid_t *__restrict__ rank, vid_t *__restrict__ rnbr, eid_t *__restrict__ cnt) {
+              const vid_t *__restrict__ rank, vid_t *__restrict__ rnbr, eid_t *__restrict__ cnt, int64_t n_all) {
     const vid_t u = bigq[blockIdx.x];
     const eid_t b = off[u], e = off[u + 1];
     const vid_t ru = rank[u];
     int c = 0;
     for (eid_t s = b + (eid_t)blockIdx.y * blockDim.x + threadIdx.x; s < e; s += (eid_t)gridDim.y * blockDim.x) {
-        const vid_t rv = rank[nbr[s]];
+        const vid_t v = nbr[s];
+        const vid_t rv = (uint64_t)v < (uint64_t)n_all ? rank[v] : -1;
         rnbr[s] = rv;
         c += rv > ru;
     }
@@ -431,26 +438,30 @@ void degree_order(const Graph &g, DevBuf<vid_t> &order, DevBuf<vid_t> &rank, int
     GMSB_CUDA(cudaStreamSynchronize(r.stream));        // ids / keys are released when this returns
 }
 
-void orient_by_rank(const Graph &g, const vid_t *rank_dev, DevBuf<eid_t> &doff, DevBuf<vid_t> &dnbr, int64_t *m_out,
-                    int *max_dplus, DevBuf<int32_t> *dplus) {
+constexpr int kBigParts = 32;                  // CTAs per big list
+
+// stage 1 of orient_by_rank over the vertex range [u_begin, u_end): needs the offsets and the slots of the range
+static void relabel_stage(const Graph &g, const vid_t *rank_dev, vid_t *rnbr, eid_t *doff, vid_t *bigq, int *nbigq,
+                          int64_t u_begin, int64_t u_end) {
     Runtime &r = rt();
-    int64_t n = g.n;
-    PhaseTrace tr("GMSB_TC_TRACE");
-    doff.alloc(n + 1);
-    doff.zero();
-    DevBuf<vid_t> rnbr(g.slots), bigq(n);
-    DevBuf<int> nbigq(1);
+    if (u_end <= u_begin) return;
+    k_relabel_count<<<grid_for(u_end - u_begin, 256), 256, 0, r.stream>>>(g.off.p, g.nbr.p, u_begin, u_end, g.n, rank_dev,
+                                                                        rnbr, doff, bigq, nbigq);
+    launched();
+}
+
+// stage 2: big lists, offsets, emit + sort
+static void finish_stage(const Graph &g, const vid_t *rank_dev, DevBuf<vid_t> &rnbr, DevBuf<vid_t> &bigq,
+                         DevBuf<int> &nbigq, DevBuf<eid_t> &doff, DevBuf<vid_t> &dnbr, int64_t *m_out, int *max_dplus,
+                         DevBuf<int32_t> *dplus, PhaseTrace &tr) {
+    Runtime &r = rt();
+    const int64_t n = g.n;
     int n_bigq = 0;
-    constexpr int kBigParts = 32;                  // CTAs per big list
     if (n) {
-        nbigq.zero();
-        k_relabel_count<<<grid_for(n, 256), 256, 0, r.stream>>>(g.off.p, g.nbr.p, n, rank_dev, rnbr.p, doff.p, bigq.p,
-                                                               nbigq.p);
-        launched();
         n_bigq = nbigq.get(0);
         if (n_bigq) {
             k_relabel_big<<<dim3((unsigned)n_bigq, kBigParts), 256, 0, r.stream>>>(bigq.p, g.off.p, g.nbr.p, rank_dev,
-                                                                                 rnbr.p, doff.p);
+                                                                                 rnbr.p, doff.p, n);
             launched();
         }
         inclusive_sum_inplace(doff.p, n + 1);
@@ -511,6 +522,40 @@ void orient_by_rank(const Graph &g, const vid_t *rank_dev, DevBuf<eid_t> &doff, 
         uint64_t *sorted = radix_sort_keys(keys.p, alt.p, m, 0, 32 + bits_for((uint64_t)(n - 1)));
         k_low32<<<grid_for(m, 256), 256, 0, r.stream>>>(sorted, m, dnbr.p); launched();
     }
+}
+
+void orient_by_rank(const Graph &g, const vid_t *rank_dev, DevBuf<eid_t> &doff, DevBuf<vid_t> &dnbr, int64_t *m_out,
+                    int *max_dplus, DevBuf<int32_t> *dplus) {
+    const int64_t n = g.n;
+    PhaseTrace tr("GMSB_TC_TRACE");
+    doff.alloc(n + 1);
+    doff.zero();
+    DevBuf<vid_t> rnbr(g.slots), bigq(n);
+    DevBuf<int> nbigq(1);
+    nbigq.zero();
+    relabel_stage(g, rank_dev, rnbr.p, doff.p, bigq.p, nbigq.p, 0, n);
+    finish_stage(g, rank_dev, rnbr, bigq, nbigq, doff, dnbr, m_out, max_dplus, dplus, tr);
+}
+
+void orient_pipeline_begin(const Graph &g, OrientPipeline &p) {
+    GMSB_REQUIRE(!g.directed, "degree orientation needs an undirected graph");
+    p.d = new Dag();
+    p.d->n = g.n;
+    degree_order(g, p.d->order, p.d->rank, &p.d->max_deg);
+    p.d->off.alloc(g.n + 1);
+    p.d->off.zero();
+    p.rnbr.alloc(g.slots);
+    p.bigq.alloc(g.n);
+    p.nbigq.alloc(1);
+    p.nbigq.zero();
+}
+void orient_pipeline_range(const Graph &g, OrientPipeline &p, int64_t u_begin, int64_t u_end) {
+    relabel_stage(g, p.d->rank.p, p.rnbr.p, p.d->off.p, p.bigq.p, p.nbigq.p, u_begin, u_end);
+}
+void orient_pipeline_finish(const Graph &g, OrientPipeline &p) {
+    PhaseTrace tr("GMSB_TC_TRACE");
+    finish_stage(g, p.d->rank.p, p.rnbr, p.bigq, p.nbigq, p.d->off, p.d->nbr, &p.d->m, &p.d->max_dplus, &p.d->dplus, tr);
+    p.rnbr.release(); p.bigq.release(); p.nbigq.release();
 }
 
 Dag *build_degree_dag(const Graph &g) {

@@ -26,10 +26,21 @@ void degree_order(const Graph &g, DevBuf<vid_t> &order, DevBuf<vid_t> &rank, int
 void orient_by_rank(const Graph &g, const vid_t *rank_dev, DevBuf<eid_t> &doff, DevBuf<vid_t> &dnbr, int64_t *m_out,
                     int *max_dplus, DevBuf<int32_t> *dplus = nullptr);
 Dag *build_degree_dag(const Graph &g);
+// Pipelined form used while a host CSR is still being uploaded (graph_build.cu): the ranking needs the offsets only,
+// and the relabel + count pass runs per vertex range as soon as that range's neighbour slots have arrived.
+struct OrientPipeline {
+    Dag *d = nullptr;
+    DevBuf<vid_t> rnbr, bigq;
+    DevBuf<int> nbigq;
+};
+void orient_pipeline_begin(const Graph &g, OrientPipeline &p);                       // offsets on the device
+void orient_pipeline_range(const Graph &g, OrientPipeline &p, int64_t u_begin, int64_t u_end);   // slots of the range too
+void orient_pipeline_finish(const Graph &g, OrientPipeline &p);                      // everything enqueued: emit + sorts
 Graph *induce_directed(const Graph &g, const vid_t *ranking_host);
 
 // graph_build.cu
 Graph *graph_from_csr_device(int64_t n, const eid_t *off, const vid_t *nbr, bool directed, bool host_src);
+Graph *graph_from_csr_host_pipelined(int64_t n, const eid_t *off, const vid_t *nbr);
 Graph *graph_from_edgelist_device(int64_t m, const vid_t *src, const vid_t *dst, bool symmetrize);
 Graph *graph_relabel_by_degree(const Graph &in);
 

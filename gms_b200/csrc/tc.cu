@@ -226,21 +226,27 @@ k_plan_scatter(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, con
     if ((threadIdx.x & 31) == 0 && hub_u) atomicAdd(&acc[0], hub_u);
 }
 
-// Order key of an item: L2 tile of its first suffix (tile-major order keeps the lists that concurrently running
-// CTAs stream inside the L2), then heaviest vertex first.
+// Order key of an item: window class, then L2 tile of its first suffix (tile-major order keeps the lists that
+// concurrently running CTAs stream inside the L2), then heaviest vertex first.  Window classes: 0 = NEAR (everything
+// after v, up to n-1, fits the small window: no element can fall outside the bitmap), 1 = small window, 2 = wide.
+constexpr int kNearWords = kSmallWindowBytes / 4 - 1;
 __global__ void k_item_keys(const Item *__restrict__ items, int64_t cnt, const uint64_t *__restrict__ desc, int64_t n,
                             int tile_shift, const eid_t *__restrict__ off, const vid_t *__restrict__ nbr,
-                            uint64_t *__restrict__ keys, unsigned long long *__restrict__ n_small,
-                            int *__restrict__ small_words) {
+                            uint64_t *__restrict__ keys, unsigned long long *__restrict__ cls_count /* 3 */,
+                            int *__restrict__ cls_words /* 3 */) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < cnt; i += (int64_t)gridDim.x * blockDim.x) {
         const Item it = items[i];
         // a slice that mixes classes has no single u-range: use its longest-suffix part (the bulk of its work)
         const int64_t d = it.begin + (it.n1 < it.count ? it.n1 : (it.n0 < it.count ? it.n0 : 0));
         const uint64_t tile = tile_shift > 0 ? (desc[d] >> kLenBits) >> tile_shift : 0;
-        const int words = (int)(((int64_t)nbr[off[it.v + 1] - 1] - it.v + 31) >> 5);
-        const bool wide = (words + 1) * 4 > kSmallWindowBytes;
-        if (!wide) { atomicAdd(n_small, 1ull); atomicMax(small_words, words); }
-        keys[i] = ((uint64_t)wide << 63) | (tile << 32) | (uint64_t)(uint32_t)(n - 1 - it.v);
+        int words = (int)(((int64_t)nbr[off[it.v + 1] - 1] - it.v + 31) >> 5);
+        // a NEAR window starts at the multiple of 32 at or below v + 1 and holds every id up to n - 1
+        const int64_t reach_words = ((n - 1 - (((int64_t)it.v + 1) & ~int64_t(31))) >> 5) + 1;
+        int cls = (words + 1) * 4 > kSmallWindowBytes ? 2 : 1;
+        if (reach_words <= kNearWords) { cls = 0; words = (int)reach_words; }
+        atomicAdd(&cls_count[cls], 1ull);
+        atomicMax(&cls_words[cls], words);
+        keys[i] = ((uint64_t)cls << 62) | ((tile & 0x3fffffffull) << 32) | (uint64_t)(uint32_t)(n - 1 - it.v);
     }
 }
 
@@ -316,6 +322,171 @@ __device__ __forceinline__ uint32_t stream_class(const uint64_t *__restrict__ dp
         }
     }
     return hits;
+}
+
+// ---- round-2 form of the streaming loops ---------------------------------------------------------------------------
+// Same schedule, fewer instructions per probe (the kernel is issue-bound: 72 % issue-active, 20.7 warp instructions per
+// 32 probes in round 1):
+//   * NEAR items — hubs whose whole possible range (v, n-1] fits the window, which is where 99 % of the work is (hubs
+//     are the last vertices in rank space) — need no clamp: every element of a suffix is inside the bitmap, and slots
+//     that are predicated off are pointed at the guard word with a constant instead of a min;
+//   * the long-suffix loop runs its full 128-element blocks without per-element bounds (one predicated tail block);
+//   * the bit is taken with a wrapping funnel shift (no `& 31`).
+// VEC adds the 128-bit form the north star asks to compare: scalar head up to the first 16-byte boundary, int4 body,
+// scalar tail.
+//     In a NEAR item the window starts at a multiple of 32 (base = (v + 1) & ~31), so the bit number inside a word is
+//     the element's own low five bits and the subtraction of the base moves into the (per-item) bitmap pointer:
+//     element e -> word (bm - base / 32)[e >> 5], bit e & 31.  SASS per probe: LDG, SHF, LOP3, LDS, SHF.W, LOP3 + IADD3 / 2.
+template <bool NEAR>
+__device__ __forceinline__ uint32_t probe2(const uint32_t *bm, uint32_t e, uint32_t base, uint32_t cap_words) {
+    if constexpr (NEAR) {
+        return __funnelshift_r(bm[e >> 5], 0u, e) & 1u;               // bm is already shifted by -base/32 words
+    } else {
+        const uint32_t x = e - base;
+        return __funnelshift_r(bm[min(x >> 5, cap_words)], 0u, x) & 1u;
+    }
+}
+
+template <int G, bool NEAR, bool VEC>
+__device__ __forceinline__ uint32_t stream_class2(const uint64_t *__restrict__ dptr, int lo, int hi, int *ticket,
+                                                  const vid_t *__restrict__ nbr, const uint32_t *bm, uint32_t base,
+                                                  uint32_t cap_words, int lane) {
+    uint32_t hits = 0;
+    if (lo >= hi) return 0;
+    // a slot that is predicated off probes the guard word: element base + 32 * cap_words (NEAR), or one that clamps
+    const uint32_t off_x = NEAR ? base + (cap_words << 5) : base - 1u;
+    constexpr int BATCH = G == 32 ? kDescChunk : 32 / G;
+    for (;;) {
+        int d0 = 0;
+        if (lane == 0) d0 = atomicAdd(ticket, BATCH);
+        d0 = __shfl_sync(0xffffffffu, d0, 0) + lo;
+        if (d0 >= hi) break;
+        if constexpr (G == 32) {
+            const int nd = min(BATCH, hi - d0);
+            const uint64_t mine = lane < nd ? __ldcs(&dptr[d0 + lane]) : 0ull;
+            for (int k = 0; k < nd; ++k) {
+                const uint64_t ds = __shfl_sync(0xffffffffu, mine, k);
+                const int64_t start = (int64_t)(ds >> kLenBits);
+                const vid_t *__restrict__ p = nbr + start;
+                int len = (int)(ds & kLenMask);
+                if constexpr (VEC) {
+                    const int head = min(len, (int)((4 - (start & 3)) & 3));      // scalars before the 16-byte boundary
+                    if (head) {
+                        const uint32_t x = lane < head ? (uint32_t)p[lane] : off_x;
+                        hits += probe2<NEAR>(bm, x, base, cap_words);
+                    }
+                    const int4 *__restrict__ pv = reinterpret_cast<const int4 *>(p + head);
+                    const int nvec = (len - head) >> 2;
+                    int i = lane;
+                    for (; i + 32 <= (nvec & ~31) + lane; i += 32) {             // full rounds: 32 x int4 = 128 elements
+                        const int4 q = pv[i];
+                        hits += probe2<NEAR>(bm, (uint32_t)q.x, base, cap_words) +
+                                probe2<NEAR>(bm, (uint32_t)q.y, base, cap_words) +
+                                probe2<NEAR>(bm, (uint32_t)q.z, base, cap_words) +
+                                probe2<NEAR>(bm, (uint32_t)q.w, base, cap_words);
+                    }
+                    if (nvec & 31) {
+                        const bool ok = i < nvec;
+                        int4 q = make_int4(0, 0, 0, 0);
+                        if (ok) q = pv[i];
+                        hits += probe2<NEAR>(bm, ok ? (uint32_t)q.x : off_x, base, cap_words) +
+                                probe2<NEAR>(bm, ok ? (uint32_t)q.y : off_x, base, cap_words) +
+                                probe2<NEAR>(bm, ok ? (uint32_t)q.z : off_x, base, cap_words) +
+                                probe2<NEAR>(bm, ok ? (uint32_t)q.w : off_x, base, cap_words);
+                    }
+                    const int done = head + (nvec << 2);
+                    if (done < len) {
+                        const uint32_t x = done + lane < len ? (uint32_t)p[done + lane] : off_x;
+                        hits += probe2<NEAR>(bm, x, base, cap_words);
+                    }
+                } else {
+                    const vid_t *__restrict__ q = p + lane;
+                    for (int t = len >> 7; t > 0; --t, q += 128) {               // full 128-element blocks, no bounds
+                        const uint32_t x0 = (uint32_t)q[0], x1 = (uint32_t)q[32],
+                                       x2 = (uint32_t)q[64], x3 = (uint32_t)q[96];
+                        hits += probe2<NEAR>(bm, x0, base, cap_words) + probe2<NEAR>(bm, x1, base, cap_words) +
+                                probe2<NEAR>(bm, x2, base, cap_words) + probe2<NEAR>(bm, x3, base, cap_words);
+                    }
+                    const int rem = len & 127;
+                    if (rem) {
+                        const uint32_t x0 = lane < rem ? (uint32_t)q[0] : off_x;
+                        const uint32_t x1 = lane + 32 < rem ? (uint32_t)q[32] : off_x;
+                        const uint32_t x2 = lane + 64 < rem ? (uint32_t)q[64] : off_x;
+                        const uint32_t x3 = lane + 96 < rem ? (uint32_t)q[96] : off_x;
+                        hits += probe2<NEAR>(bm, x0, base, cap_words) + probe2<NEAR>(bm, x1, base, cap_words) +
+                                probe2<NEAR>(bm, x2, base, cap_words) + probe2<NEAR>(bm, x3, base, cap_words);
+                    }
+                }
+            }
+        } else {
+            const int idx = d0 + lane / G, sub = lane % G;
+            const uint64_t ds = idx < hi ? __ldcs(&dptr[idx]) : 0ull;
+            const vid_t *__restrict__ p = nbr + (ds >> kLenBits);
+            const int len = (int)(ds & kLenMask);
+            if constexpr (G == 1) {
+#pragma unroll
+                for (int j = 0; j < kShortLen; ++j)
+                    hits += probe2<NEAR>(bm, j < len ? (uint32_t)p[j] : off_x, base, cap_words);
+            } else {
+                for (int j = sub; j < len; j += 4 * G) {
+                    const uint32_t x0 = (uint32_t)p[j];
+                    const uint32_t x1 = j + G < len ? (uint32_t)p[j + G] : off_x;
+                    const uint32_t x2 = j + 2 * G < len ? (uint32_t)p[j + 2 * G] : off_x;
+                    const uint32_t x3 = j + 3 * G < len ? (uint32_t)p[j + 3 * G] : off_x;
+                    hits += probe2<NEAR>(bm, x0, base, cap_words) + probe2<NEAR>(bm, x1, base, cap_words) +
+                            probe2<NEAR>(bm, x2, base, cap_words) + probe2<NEAR>(bm, x3, base, cap_words);
+                }
+            }
+        }
+    }
+    return hits;
+}
+
+// VAR 0: the round-1 loops (stream_class); 1: stream_class2; 2: stream_class2 with the 128-bit body
+template <int BLOCK, int MINB, int VAR, bool NEAR>
+__global__ void __launch_bounds__(BLOCK, MINB)
+k_tc_bitmap2(const Item *__restrict__ items, int64_t first, int64_t stride, int64_t count, uint32_t cap_words,
+             const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, const uint64_t *__restrict__ desc,
+             unsigned long long *__restrict__ total, unsigned int *__restrict__ ticket) {
+    extern __shared__ uint32_t bm[];                  // cap_words + 1 words
+    __shared__ unsigned long long red[BLOCK / 32];
+    __shared__ unsigned int s_item;
+    __shared__ int s_next[3];
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (uint32_t i = tid; i <= cap_words; i += BLOCK) bm[i] = 0u;
+    unsigned long long hits64 = 0;
+    for (;;) {
+        if (tid == 0) { s_item = atomicAdd(ticket, 1u); s_next[0] = 0; s_next[1] = 0; s_next[2] = 0; }
+        __syncthreads();                              // ticket visible; previous item's clears done
+        const int64_t it = (int64_t)s_item;
+        if (it >= count) break;
+        const Item item = items[first + it * stride];                     // plan order: L2 tile, then heaviest
+        const vid_t v = item.v;
+        const eid_t ob = off[v], oe = off[v + 1];
+        const uint32_t base = NEAR ? (((uint32_t)v + 1u) & ~31u) : (uint32_t)v + 1u;       // first element of the window
+        for (eid_t j = ob + tid; j < oe; j += BLOCK) {
+            const uint32_t x = (uint32_t)nbr[j] - base;
+            atomicOr(&bm[x >> 5], 1u << (x & 31));
+        }
+        __syncthreads();                              // bitmap of N+(v) complete
+        const uint64_t *__restrict__ dptr = desc + item.begin;
+        uint32_t hits;
+        if constexpr (VAR == 0) {
+            hits = stream_class<32>(dptr, item.n1, item.count, &s_next[2], nbr, bm, base, cap_words, lane);
+            hits += stream_class<8>(dptr, item.n0, item.n1, &s_next[1], nbr, bm, base, cap_words, lane);
+            hits += stream_class<1>(dptr, 0, item.n0, &s_next[0], nbr, bm, base, cap_words, lane);
+        } else {
+            const uint32_t *bmv = NEAR ? bm - (base >> 5) : bm;       // NEAR: indexed by the element's own word number
+            hits = stream_class2<32, NEAR, VAR == 2>(dptr, item.n1, item.count, &s_next[2], nbr, bmv, base, cap_words, lane);
+            hits += stream_class2<8, NEAR, false>(dptr, item.n0, item.n1, &s_next[1], nbr, bmv, base, cap_words, lane);
+            hits += stream_class2<1, NEAR, false>(dptr, 0, item.n0, &s_next[0], nbr, bmv, base, cap_words, lane);
+        }
+        hits64 += hits;
+        __syncthreads();                              // every probe of this item done
+        for (eid_t j = ob + tid; j < oe; j += BLOCK) bm[((uint32_t)nbr[j] - base) >> 5] = 0u;
+    }
+    unsigned long long s = block_sum(hits64, red);
+    if (tid == 0 && s) atomicAdd(total, s);
 }
 
 template <int BLOCK, int MINB, bool DEEP = false>
@@ -491,14 +662,17 @@ TcPlan *build_plan(const Dag &d, const gmsb_tc_options &opt) {
             DevBuf<uint64_t> ik(p->n_items), ik2(p->n_items);
             DevBuf<Item> items2(p->n_items);
             const int tile_shift = opt.reserved[1] > 0 ? opt.reserved[1] : (opt.reserved[1] < 0 ? 0 : 24);
-            DevBuf<unsigned long long> nsm(1);
-            DevBuf<int> smw(1);
-            nsm.zero(); smw.zero();
+            DevBuf<unsigned long long> ccnt(3);
+            DevBuf<int> cwords(3);
+            ccnt.zero(); cwords.zero();
             k_item_keys<<<grid_for(p->n_items, 256), 256, 0, r.stream>>>(p->items.p, p->n_items, p->desc.p, n,
-                                                                        tile_shift, d.off.p, d.nbr.p, ik.p, nsm.p, smw.p);
+                                                                        tile_shift, d.off.p, d.nbr.p, ik.p, ccnt.p,
+                                                                        cwords.p);
             launched();
-            p->n_items_small = (int64_t)nsm.get(0);
-            p->small_span_words = smw.get(0);
+            unsigned long long h_cc[3];
+            ccnt.download(h_cc, 3);
+            cwords.download(p->cls_words, 3);
+            for (int c = 0; c < 3; ++c) p->cls_items[c] = (int64_t)h_cc[c];
             size_t bytes = 0;
             GMSB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, ik.p, ik2.p, p->items.p, items2.p, p->n_items, 0,
                                                       64, r.stream));
@@ -524,7 +698,7 @@ gmsb_tc_options normalise_tc_options(const gmsb_tc_options *in) { return normali
 TcPlan &ensure_plan(Graph &g, const gmsb_tc_options &opt) {
     GMSB_REQUIRE(!g.directed, "triangle kernels need an undirected graph");
     GMSB_REQUIRE(opt.variant >= GMSB_TC_AUTO && opt.variant <= GMSB_TC_BITMAP, "tc: bad variant");
-    if (!opt.reuse_plan) { delete g.dag; g.dag = nullptr; }
+    if (!opt.reuse_plan && !g.dag_pinned) { delete g.dag; g.dag = nullptr; }
     if (!g.dag) g.dag = build_degree_dag(g);
     Dag &d = *g.dag;
     if (d.plan && !same_plan(d.plan->opt, opt)) { delete_plan(d.plan); d.plan = nullptr; }
@@ -556,7 +730,7 @@ void tc_total(Graph &g, const gmsb_tc_options &opt_in, uint64_t *out, gmsb_tc_st
     t_bm.start();
     if (my_items) {
         GMSB_REQUIRE(p.n_items < (int64_t(1) << 31), "tc: too many bitmap items");
-        DevBuf<unsigned int> tickets(2);
+        DevBuf<unsigned int> tickets(3);
         tickets.zero();
         // one persistent wave per window class (the ticket's free is stream-ordered after the kernels)
         auto launch = [&](auto kern, int BLOCK, const Item *items, int64_t cnt, int cap_words, unsigned int *ticket) {
@@ -573,13 +747,23 @@ void tc_total(Graph &g, const gmsb_tc_options &opt_in, uint64_t *out, gmsb_tc_st
                                                   p.desc.p, total.p, ticket);
             launched();
         };
-        const int shape = opt.reserved[2];              // experiments: one launch with another CTA shape
+        // One persistent wave per window class.  reserved[2] (A/B runs): 0 = round-2 loops, 7 = round-2 loops with the
+        // 128-bit body, 8 = round-1 loops; 1..6 = round-1 kernel with one launch and another CTA shape.
+        const int shape = opt.reserved[2];
+        const Item *it0 = p.items.p, *it1 = it0 + p.cls_items[0], *it2 = it1 + p.cls_items[1];
+        const int wsmall = std::max(p.cls_words[0], p.cls_words[1]);
         if (shape == 0) {
-            // small windows (<= 55 KB of bitmap): four CTAs of 512 threads per SM = 64 resident warps
-            launch(k_tc_bitmap<512, 4>, 512, p.items.p, p.n_items_small, p.small_span_words, tickets.p);
-            // wide windows: three CTAs per SM
-            launch(k_tc_bitmap<512, 3>, 512, p.items.p + p.n_items_small, p.n_items - p.n_items_small,
-                   p.max_span_words, tickets.p + 1);
+            launch(k_tc_bitmap2<512, 4, 1, true>, 512, it0, p.cls_items[0], p.cls_words[0], tickets.p);
+            launch(k_tc_bitmap2<512, 4, 1, false>, 512, it1, p.cls_items[1], p.cls_words[1], tickets.p + 1);
+            launch(k_tc_bitmap2<512, 3, 1, false>, 512, it2, p.cls_items[2], p.cls_words[2], tickets.p + 2);
+        } else if (shape == 7) {
+            launch(k_tc_bitmap2<512, 4, 2, true>, 512, it0, p.cls_items[0], p.cls_words[0], tickets.p);
+            launch(k_tc_bitmap2<512, 4, 2, false>, 512, it1, p.cls_items[1], p.cls_words[1], tickets.p + 1);
+            launch(k_tc_bitmap2<512, 3, 2, false>, 512, it2, p.cls_items[2], p.cls_words[2], tickets.p + 2);
+        } else if (shape == 8) {
+            // small windows (<= 55 KB of bitmap): four CTAs of 512 threads per SM = 64 resident warps; wide: three
+            launch(k_tc_bitmap<512, 4>, 512, it0, p.cls_items[0] + p.cls_items[1], wsmall, tickets.p);
+            launch(k_tc_bitmap<512, 3>, 512, it2, p.cls_items[2], p.cls_words[2], tickets.p + 1);
         } else if (shape == 1) launch(k_tc_bitmap<256, 6>, 256, p.items.p, p.n_items, p.max_span_words, tickets.p);
         else if (shape == 2) launch(k_tc_bitmap<1024, 1>, 1024, p.items.p, p.n_items, p.max_span_words, tickets.p);
         else if (shape == 3) launch(k_tc_bitmap<512, 4>, 512, p.items.p, p.n_items, p.max_span_words, tickets.p);
@@ -628,7 +812,10 @@ void tc_total(Graph &g, const gmsb_tc_options &opt_in, uint64_t *out, gmsb_tc_st
         s.bitmap_smem_bytes = (p.max_span_words + 1) * 4;
         *stats = s;
     }
-    if (!opt.reuse_plan) { delete g.dag; g.dag = nullptr; }
+    if (!opt.reuse_plan) {
+        if (g.dag_pinned) { delete_plan(g.dag->plan); g.dag->plan = nullptr; }
+        else { delete g.dag; g.dag = nullptr; }
+    }
 }
 
 }  // namespace gmsb

@@ -31,10 +31,10 @@ struct TcPlan {
     DevBuf<Item> items;                 // bitmap work items
     int64_t n_items = 0;
     int max_span_words = 0;
-    // items are ordered small-window first: [0, n_items_small) fit kSmallWindowBytes of bitmap, which lets four
-    // CTAs share an SM (64 resident warps); the few wide-window hubs run in a second launch with three
-    int64_t n_items_small = 0;
-    int small_span_words = 0;
+    // items are ordered by window class: NEAR (the whole range after v up to n-1 fits the small window: no clamp in
+    // the probe), small window (kSmallWindowBytes of bitmap: four CTAs per SM, 64 resident warps), wide (three per SM)
+    int64_t cls_items[3] = {0, 0, 0};
+    int cls_words[3] = {0, 0, 0};
     DevBuf<uint64_t> m_desc, g_desc;    // light edges for merge / gallop
     DevBuf<vid_t> m_v, g_v;
     int64_t n_merge = 0, n_gallop = 0, n_bitmap_edges = 0;

@@ -70,6 +70,14 @@ GMSB_API int gmsb_generate_uniform(int scale, int64_t m, int32_t *src, int32_t *
 GMSB_API int gmsb_graph_from_csr(int64_t n, const int64_t *offsets, const int32_t *nbrs, int directed, gmsb_graph_t *out);
 GMSB_API int gmsb_graph_from_csr_device(int64_t n, const int64_t *offsets, const int32_t *nbrs, int directed,
                                gmsb_graph_t *out);
+/* Same, with construction flags.  GMSB_BUILD_ORIENT (undirected graphs): the degree-oriented representation that
+ * the triangle / clique / similarity entry points work on is built together with the graph — BenchmarkKernelBk calls
+ * SGraph::FromCGraph once and then the kernel (gms/common/benchmark.h:105-118); here the upload of the host arrays is
+ * chunked and the ranking, validation and relabelling passes run on the chunks that have already arrived.  Use pinned
+ * host memory for the copies to overlap. */
+typedef enum { GMSB_BUILD_DEFAULT = 0, GMSB_BUILD_ORIENT = 1 } gmsb_build_flags;
+GMSB_API int gmsb_graph_from_csr_ex(int64_t n, const int64_t *offsets, const int32_t *nbrs, int directed, int flags,
+                                    gmsb_graph_t *out);
 /* BuilderBase::MakeGraphFromEL + SquishGraph            gms/third_party/gapbs/builder.h:279-298,237-251
  * n = max id + 1; symmetrize inserts both directions; lists sorted, de-duplicated, self loops removed —
  * done by an on-GPU radix sort of 64-bit (u<<32|v) keys. */
@@ -168,6 +176,43 @@ GMSB_API int gmsb_union_batch(gmsb_graph_t g, int64_t npairs, const int32_t *a, 
 /* SortedSetBase::union_count                            gms/representations/sets/sorted_set.h:140
  * out[i] = |N(a[i]) ∪ N(b[i])| */
 GMSB_API int gmsb_union_count_batch(gmsb_graph_t g, int64_t npairs, const int32_t *a, const int32_t *b, uint64_t *out);
+
+/* ---- device-resident sets: the Set concept as an object -------------------------------------------------------------- */
+/* SortedSetBase<int32_t> / SortedSetRefBase<int32_t>        gms/representations/sets/sorted_set.h:22-270, sorted_set_ref.h:10-80
+ * An ascending, duplicate-free int32 set in device memory.  Binary operations take set HANDLES and leave their result
+ * on the device, so chains like Bron-Kerbosch's P ∩ N(v), X ∩ N(v), P \ {v} (maximal_clique_enum/sequential/tomita.h)
+ * never return to the host.  include/gms_b200/cuda_sorted_set.hpp wraps these in a move-only class with the
+ * reference's member names. */
+typedef struct gmsb_set_s *gmsb_set_t;
+typedef enum { GMSB_SET_INTERSECT = 0, GMSB_SET_UNION = 1, GMSB_SET_DIFFERENCE = 2 } gmsb_set_op_kind;
+/* SortedSetBase(const SetElement*, size_t): sorts what it is given   sorted_set.h:64-66 */
+GMSB_API int gmsb_set_from_host(const int32_t *elems, int64_t count, gmsb_set_t *out);
+/* SortedSetBase::Range(bound) = {0 .. bound-1}                       sorted_set.h:246-251 */
+GMSB_API int gmsb_set_range(int64_t bound, gmsb_set_t *out);
+/* SetGraph::out_neigh(v) as a borrowed view of the graph's CSR (SortedSetRef); the graph must outlive the view.
+ * Modifying operations on a view first turn it into an owning set. */
+GMSB_API int gmsb_set_neighbourhood(gmsb_graph_t g, int32_t v, gmsb_set_t *out);
+GMSB_API int gmsb_set_clone(gmsb_set_t a, gmsb_set_t *out);                          /* sorted_set.h:245 */
+GMSB_API int gmsb_set_free(gmsb_set_t a);
+GMSB_API int gmsb_set_cardinality(gmsb_set_t a, int64_t *n);                         /* sorted_set.h:253 */
+GMSB_API int gmsb_set_to_host(gmsb_set_t a, int32_t *out);                           /* toArray, sorted_set.h:258-262 */
+GMSB_API int gmsb_set_contains(gmsb_set_t a, int32_t x, int *flag);                  /* sorted_set.h:216-220 */
+GMSB_API int gmsb_set_add(gmsb_set_t a, int32_t x);                                  /* add / union_inplace(elem) :222-231 */
+GMSB_API int gmsb_set_remove(gmsb_set_t a, int32_t x);                               /* remove / difference_inplace(elem) :233-243 */
+GMSB_API int gmsb_set_equal(gmsb_set_t a, gmsb_set_t b, int *flag);                  /* operator== :255 */
+/* a op b as a new device set: intersect :160-166, union_with :104-109, difference :184-189 */
+GMSB_API int gmsb_set_op(int op, gmsb_set_t a, gmsb_set_t b, gmsb_set_t *out);
+/* a <- a op b: intersect_inplace :168-174, union_inplace :118-124, difference_inplace :198-204 */
+GMSB_API int gmsb_set_op_inplace(int op, gmsb_set_t a, gmsb_set_t b);
+/* |a op b|: intersect_count :176-182, union_count :140 */
+GMSB_API int gmsb_set_op_count(int op, gmsb_set_t a, gmsb_set_t b, uint64_t *out);
+/* one left set against a batch of right sets, one launch: out[i] = |a op bs[i]| / outs[i] = a op bs[i] (device sets) */
+GMSB_API int gmsb_set_op_count_many(int op, gmsb_set_t a, int64_t count, const gmsb_set_t *bs, uint64_t *out);
+GMSB_API int gmsb_set_op_many(int op, gmsb_set_t a, int64_t count, const gmsb_set_t *bs, gmsb_set_t *outs);
+/* out[i] = |a op N(members[i])| for every member of the set `members` (ascending): the pivot scoring loop of Tomita's
+ * Bron-Kerbosch (tomita.h:17-31, cand.intersect_count(graph.out_neigh(v))) and the pull step of the approximate
+ * degeneracy order (degeneracy_approx_set.h:77) as one launch. */
+GMSB_API int gmsb_set_op_count_neighbourhoods(int op, gmsb_set_t a, gmsb_graph_t g, gmsb_set_t members, uint64_t *out);
 
 /* ---- vertex similarity ------------------------------------------------------------------------------------------------ */
 /* GMS::VertexSim::Metric                                gms/algorithms/set_based/vertex_similarity/vertex_similarity.h:18 */

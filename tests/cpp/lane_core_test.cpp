@@ -42,6 +42,50 @@ static u64 run_lanes(const std::vector<u64> &cm, int pitch, int c, int need, int
     return total;
 }
 
+// The flat form (FlatState / flat_refill / flat_step) driven the way kclique_lane.cuh: lane_tasks_flat drives it: 32 lane
+// states, refills batched by flat_should_refill, one leaf operation per lane and iteration.
+template <int NW>
+static u64 run_flat(const std::vector<u64> &cm, int pitch, int c, int need, int split_log2) {
+    FlatState<NW> s[32];
+    for (auto &x : s) flat_init<NW>(x);
+    unsigned counter = 0;
+    const unsigned t_end = (unsigned)c << split_log2;
+    u64 total = 0;
+    for (;;) {
+        int want = 0, live = 0;
+        bool dry[32];
+        for (int l = 0; l < 32; ++l) {
+            dry[l] = s[l].w1 >= NW;
+            want += dry[l] && !s[l].exhausted;
+            live += !dry[l];
+        }
+        if (flat_should_refill(want, live)) {
+            for (int l = 0; l < 32; ++l)
+                if (dry[l] && !s[l].exhausted) {
+                    flat_refill<NW>(s[l], cm.data(), pitch, need, split_log2, t_end, &counter, nullptr);
+                    flat_skip<NW>(s[l]);
+                }
+            continue;
+        }
+        if (live == 0) break;
+        for (int l = 0; l < 32; ++l)
+            for (int r = 0; r < 4; ++r)                       // kFlatBurst
+                if (s[l].w1 < NW) {
+                    total += flat_step<NW>(s[l], cm.data(), pitch);
+                    if (s[l].bits == 0) flat_skip<NW>(s[l]);
+                }
+    }
+    return total;
+}
+static u64 run_flat_any(int nwb, const std::vector<u64> &cm, int pitch, int c, int need, int sl) {
+    switch (nwb) {
+        case 1: return run_flat<1>(cm, pitch, c, need, sl);
+        case 2: return run_flat<2>(cm, pitch, c, need, sl);
+        case 3: return run_flat<3>(cm, pitch, c, need, sl);
+        default: return run_flat<4>(cm, pitch, c, need, sl);
+    }
+}
+
 static u64 run_any(int nwb, const std::vector<u64> &cm, int pitch, int c, int need, int sl) {
     switch (nwb) {
         case 1: return run_lanes<1>(cm, pitch, c, need, sl);
@@ -97,6 +141,14 @@ int main() {
                     if (got != want) {
                         ++fails;
                         std::printf("FAIL lane c=%d p=%.2f need=%d split=%d got=%llu want=%llu\n", c, p, need, sl, got, want);
+                    }
+                    if (nwb <= 4) {
+                        const u64 gf = run_flat_any(nwb, cm, pitch, c, need, sl);
+                        ++checks;
+                        if (gf != want) {
+                            ++fails;
+                            std::printf("FAIL flat c=%d p=%.2f need=%d split=%d got=%llu want=%llu\n", c, p, need, sl, gf, want);
+                        }
                     }
                 }
             }

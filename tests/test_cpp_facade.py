@@ -32,6 +32,24 @@ def test_facade_on_gpu(gms):
     assert "all checks passed" in r.stdout
 
 
+def test_sets_facade_compiles_and_fails_loudly_without_gpu(gms):
+    exe = build(os.path.join(ROOT, "tests", "cpp", "sets_test.cpp"), os.path.join(ROOT, "build", "sets_test"))
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe], capture_output=True, text=True)
+        assert r.returncode == 3 and "CUDA" in r.stderr
+
+
+@pytest.mark.gpu
+def test_reference_set_cases_on_gpu(gms):
+    """testing/sets.cpp (54 typed cases) with CudaSortedSet as the set type, plus Tomita's pivot rule and one
+    Bron-Kerbosch expansion written against the Set concept."""
+    exe = build(os.path.join(ROOT, "tests", "cpp", "sets_test.cpp"), os.path.join(ROOT, "build", "sets_test"))
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "all checks passed" in r.stdout
+
+
 @pytest.mark.gpu
 def test_example_on_gpu(gms):
     exe = build(os.path.join(ROOT, "examples", "triangle_counting.cpp"), os.path.join(ROOT, "build", "triangle_counting"))

@@ -175,3 +175,73 @@ def test_large_host_csr_sorted_unsorted_and_malformed(gms):
     bad[-1] = g.n                                                           # id out of range in the last slot
     with pytest.raises(gms.GmsbError):
         gms.Graph.from_csr(off, bad)
+
+
+def test_pipelined_upload_builds_the_same_representation(gms, orc):
+    """gmsb_graph_from_csr_ex(GMSB_BUILD_ORIENT): chunked upload with the ranking / validation / relabel passes running
+    on the chunks that have arrived.  Same counts, same exported CSR, same error behaviour as gmsb_graph_from_csr."""
+    s, d = gms.generate_rmat(16)
+    g = gms.Graph.from_edgelist(s, d, True)
+    off, nbr = g.export_csr()
+    gp = gms.Graph.from_csr(off, nbr, orient=True)
+    assert gp.tc_total_ex(reuse_plan=False)[0] == 15656287                # SURVEY.md 8c, kronecker-16
+    assert gp.tc_total_ex(reuse_plan=False)[0] == 15656287                # the pinned DAG survives reuse_plan = 0
+    assert (gp.tc_vertex2() == g.tc_vertex2()).all()
+    assert gp.kclique_count(4) == 291383976
+    eo, en = gp.export_csr()
+    assert (eo == off).all() and (en == nbr).all()
+    # unsorted lists: sorted on the way in, DAG unaffected
+    rng = np.random.default_rng(1)
+    shuffled = nbr.copy()
+    for u in rng.integers(0, len(off) - 1, 500):
+        rng.shuffle(shuffled[off[u]:off[u + 1]])
+    gs = gms.Graph.from_csr(off, shuffled, orient=True)
+    eo, en = gs.export_csr()
+    assert (en == nbr).all() and gs.tc_total() == 15656287
+    # malformed inputs are rejected, and the library keeps working afterwards
+    bad = nbr.copy()
+    bad[len(bad) // 2] = g.n + 7
+    with pytest.raises(gms.GmsbError):
+        gms.Graph.from_csr(off, bad, orient=True)
+    bad[len(bad) // 2] = -3
+    with pytest.raises(gms.GmsbError):
+        gms.Graph.from_csr(off, bad, orient=True)
+    bad_off = off.copy()
+    bad_off[7] = bad_off[-1] + 1000
+    with pytest.raises(gms.GmsbError):
+        gms.Graph.from_csr(bad_off, nbr, orient=True)
+    assert gms.Graph.from_csr(off, nbr, orient=True).tc_total() == 15656287
+    # small and empty graphs take the plain path
+    tri = gms.Graph.from_csr(np.array([0, 2, 4, 6], np.int64), np.array([1, 2, 0, 2, 0, 1], np.int32), orient=True)
+    assert tri.tc_total() == 1
+    assert gms.Graph.from_csr(np.array([0, 0, 0], np.int64), np.zeros(0, np.int32), orient=True).tc_total() == 0
+
+
+def test_offsets_beyond_the_neighbour_array_are_rejected(gms):
+    """offsets such as [0, 1e9, 5] pass 'starts at 0, ends at slots' — every entry has to be bounded."""
+    nbr = np.array([1, 0, 2, 1, 0], np.int32)
+    for off in ([0, 10**9, 5], [0, 6, 5], [0, -1, 5]):
+        with pytest.raises(gms.GmsbError):
+            gms.Graph.from_csr(np.array(off, np.int64), nbr)
+    g = gms.Graph.from_csr(np.array([0, 2, 4, 6], np.int64), np.array([1, 2, 0, 2, 0, 1], np.int32))
+    assert g.tc_total() == 1
+
+
+def test_cliques_on_a_dag_whose_arcs_descend(gms, orc):
+    """KcListing accepts any DAG; a directed handle whose arcs go from higher to lower ids (or both ways)
+    must give the same counts as the ascending orientation."""
+    s, d = random_graph_edges(5, 300, 9000, skew=0.6)
+    g = gms.Graph.from_edgelist(s, d, True)
+    want = {k: g.kclique_count(k) for k in (3, 4, 5)}
+    off, nbr = g.export_csr()
+    n = g.n
+    src = np.repeat(np.arange(n, dtype=np.int32), np.diff(off))
+    down = src > nbr                                         # every edge once, pointing to the lower id
+    dag_down = gms.Graph.from_edgelist(src[down], nbr[down], False)
+    rng = np.random.default_rng(3)
+    order = rng.permutation(n)                               # an arbitrary acyclic orientation
+    mixed = order[src] < order[nbr]
+    dag_mixed = gms.Graph.from_edgelist(src[mixed], nbr[mixed], False)
+    for k, w in want.items():
+        assert dag_down.kclique_count(k) == w, k
+        assert dag_mixed.kclique_count(k) == w, k

@@ -19,6 +19,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scale", type=int, default=24)
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--orient", type=int, default=1, help="1: gmsb_graph_from_csr_ex(GMSB_BUILD_ORIENT)")
     args = ap.parse_args()
     G.set_device(0)
     src, dst = G.generate_rmat(args.scale)
@@ -32,12 +33,12 @@ def main():
     for rep in range(args.reps):
         print(f"--- rep {rep}", file=sys.stderr, flush=True)
         t0 = time.perf_counter()
-        gg = G.Graph.from_csr(off_h.numpy(), nbr_h.numpy()[:slots])
+        gg = G.Graph.from_csr(off_h.numpy(), nbr_h.numpy()[:slots], orient=bool(args.orient))
         t1 = time.perf_counter()
         c, st = gg.tc_total_ex(reuse_plan=False)
         t2 = time.perf_counter()
         gg.free()
-        print(json.dumps({"scale": args.scale, "rep": rep, "from_csr_ms": round((t1 - t0) * 1e3, 2),
+        print(json.dumps({"scale": args.scale, "orient_with_upload": args.orient, "rep": rep, "from_csr_ms": round((t1 - t0) * 1e3, 2),
                           "tc_total_ms": round((t2 - t1) * 1e3, 2), "triangles": c,
                           "ms_orient": round(st["ms_orient"], 2), "ms_count": round(st["ms_count"], 2),
                           "ms_bitmap": round(st["ms_bitmap"], 2), "n_items": st["bitmap_items"],
