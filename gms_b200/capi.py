@@ -53,6 +53,11 @@ SIGNATURES = {
     "gmsb_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "gmsb_set_device": (C.c_int, [C.c_int]),
     "gmsb_set_stream": (C.c_int, [C.c_void_p]),
+    "gmsb_set_devices": (C.c_int, [C.c_int, C.POINTER(C.c_int)]),
+    "gmsb_tc_total_multi": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "gmsb_tc_vertex2_multi": (C.c_int, [C.c_void_p, _i64p]),
+    "gmsb_kclique_count_multi": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]),
+    "gmsb_edge_similarity_multi": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int64)]),
     "gmsb_synchronize": (C.c_int, []),
     "gmsb_trim_memory": (C.c_int, []),
     "gmsb_launch_count": (C.c_int, [C.POINTER(C.c_uint64)]),
@@ -73,6 +78,7 @@ SIGNATURES = {
     "gmsb_order_degree": (C.c_int, [C.c_void_p, C.c_int, _i32p]),
     "gmsb_order_degeneracy": (C.c_int, [C.c_void_p, _i32p]),
     "gmsb_order_degeneracy_approx": (C.c_int, [C.c_void_p, C.c_double, C.c_int, _i32p]),
+    "gmsb_order_degeneracy_approx_ex": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int, C.c_uint64, _i32p]),
     "gmsb_graph_worth_relabelling": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "gmsb_orient": (C.c_int, [C.c_void_p, _i32p, C.POINTER(C.c_void_p)]),
     "gmsb_tc_total": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
@@ -138,6 +144,12 @@ def device_count():
 
 def set_device(i):
     _check(lib().gmsb_set_device(i))
+
+
+def set_devices(ids):
+    """The devices of the *_multi entry points (one process, several GPUs); ids[0] becomes the primary device."""
+    arr = (C.c_int * len(ids))(*ids)
+    _check(lib().gmsb_set_devices(len(ids), arr))
 
 
 def set_stream(ptr):
@@ -271,6 +283,13 @@ class Graph:
         _check(lib().gmsb_order_degeneracy_approx(self.h, float(epsilon), int(rank_format), out))
         return out[:self.n]
 
+    def degeneracy_order_approx_ex(self, epsilon=1.0, rank_format=False, boundary="average", pull=False, seed=1):
+        kinds = {"average": 0, "min": 1, "prob_min": 2, "prob_median": 3}
+        out = np.zeros(max(self.n, 1), np.int32)
+        _check(lib().gmsb_order_degeneracy_approx_ex(self.h, float(epsilon), int(rank_format), kinds[boundary], int(pull),
+                                                     seed, out))
+        return out[:self.n]
+
     def worth_relabelling(self):
         v = C.c_int(0)
         _check(lib().gmsb_graph_worth_relabelling(self.h, C.byref(v)))
@@ -288,10 +307,11 @@ class Graph:
         return out.value
 
     def tc_total_ex(self, variant="auto", part_index=0, part_count=1, reuse_plan=False, hub_bitmap_bits=0,
-                    gallop_ratio=0, hub_min_work=0, item_cost=0, tile_shift=0, cta_shape=0):
-        """item_cost / tile_shift / cta_shape are tuning knobs carried in gmsb_tc_options.reserved[0..2]."""
+                    gallop_ratio=0, hub_min_work=0, item_cost=0, tile_shift=0, cta_shape=0, merge_impl=0):
+        """item_cost / tile_shift / cta_shape / merge_impl are tuning knobs carried in gmsb_tc_options.reserved[0..3]
+        (merge_impl = 1: the block-compare kernel for the balanced light pairs instead of the merge path; measured slower)."""
         opt = TcOptions(TC_VARIANTS[variant], part_index, part_count, int(reuse_plan), hub_bitmap_bits, gallop_ratio,
-                        hub_min_work, (C.c_int32 * 4)(item_cost, tile_shift, cta_shape, 0))
+                        hub_min_work, (C.c_int32 * 4)(item_cost, tile_shift, cta_shape, merge_impl))
         out, st = C.c_uint64(0), TcStats()
         _check(lib().gmsb_tc_total_ex(self.h, C.byref(opt), C.byref(out), C.byref(st)))
         return out.value, st.as_dict()
@@ -343,6 +363,29 @@ class Graph:
         _check(lib().gmsb_edge_similarity(self.h, SIM_METRICS[metric], None, C.byref(m)))
         out = np.zeros(max(m.value, 1), np.float64)
         _check(lib().gmsb_edge_similarity(self.h, SIM_METRICS[metric], out.ctypes.data, C.byref(m)))
+        return out[:m.value]
+
+    # --- several GPUs in one process (after gms_b200.set_devices)
+    def tc_total_multi(self):
+        out = C.c_uint64(0)
+        _check(lib().gmsb_tc_total_multi(self.h, C.byref(out)))
+        return out.value
+
+    def tc_vertex2_multi(self):
+        out = np.zeros(max(self.n, 1), np.int64)
+        _check(lib().gmsb_tc_vertex2_multi(self.h, out))
+        return out[:self.n]
+
+    def kclique_count_multi(self, k):
+        out = C.c_uint64(0)
+        _check(lib().gmsb_kclique_count_multi(self.h, k, C.byref(out)))
+        return out.value
+
+    def edge_similarity_multi(self, metric):
+        m = C.c_int64(0)
+        _check(lib().gmsb_edge_similarity_multi(self.h, SIM_METRICS[metric], None, C.byref(m)))
+        out = np.zeros(max(m.value, 1), np.float64)
+        _check(lib().gmsb_edge_similarity_multi(self.h, SIM_METRICS[metric], out.ctypes.data, C.byref(m)))
         return out[:m.value]
 
     # --- cliques

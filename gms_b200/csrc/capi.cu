@@ -16,41 +16,57 @@ namespace gmsb {
 
 namespace {
 thread_local std::string g_last_error;
-Runtime g_rt;
-bool g_rt_ready = false;
+// One Runtime per device.  A host thread works on its bound device (bind_device: the workers of the multi-GPU entry
+// points, mgpu.cu) or, by default, on the process's primary device (gmsb_set_device).
+constexpr int kMaxDevices = 64;
+Runtime g_rts[kMaxDevices];
+bool g_rt_ready[kMaxDevices] = {};
 int g_device = 0;
+thread_local int t_device = -1;
 std::mutex g_rt_mutex;
 }  // namespace
 
 void set_last_error(const std::string &msg) { g_last_error = msg; }
+const std::string &last_error_message() { return g_last_error; }
+
+int current_device() { return t_device >= 0 ? t_device : g_device; }
+void bind_device(int device) {
+    t_device = device;
+    if (device >= 0) cudaSetDevice(device);
+}
 
 Runtime &rt() {
-    if (!g_rt_ready) {
+    const int dev = current_device();
+    if (dev < 0 || dev >= kMaxDevices) throw Error(GMSB_ERR_INVALID, "device index out of range");
+    if (!g_rt_ready[dev]) {
         std::lock_guard<std::mutex> lock(g_rt_mutex);
-        if (!g_rt_ready) {
+        if (!g_rt_ready[dev]) {
             int count = 0;
             cudaError_t e = cudaGetDeviceCount(&count);
             if (e != cudaSuccess || count == 0)
                 throw Error(GMSB_ERR_CUDA, std::string("no usable CUDA device (") +
                                                (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
                                                "); gms-b200 has no CPU fallback");
-            GMSB_CUDA(cudaSetDevice(g_device));
+            GMSB_REQUIRE(dev < count, "device index beyond the visible devices");
+            GMSB_CUDA(cudaSetDevice(dev));
             cudaDeviceProp prop{};
-            GMSB_CUDA(cudaGetDeviceProperties(&prop, g_device));
-            g_rt.device = g_device;
-            g_rt.sm_count = prop.multiProcessorCount;
-            g_rt.smem_optin = prop.sharedMemPerBlockOptin;
-            g_rt_ready = true;
+            GMSB_CUDA(cudaGetDeviceProperties(&prop, dev));
+            g_rts[dev].device = dev;
+            g_rts[dev].sm_count = prop.multiProcessorCount;
+            g_rts[dev].smem_optin = prop.sharedMemPerBlockOptin;
+            g_rt_ready[dev] = true;
         }
     }
-    return g_rt;
+    return g_rts[dev];
 }
 
 // ---- caching device arena ------------------------------------------------------------------------------------------
+// Free lists are kept per device: a block cached by one device is never handed to a kernel on another one.
 namespace {
 std::mutex g_arena_mutex;
-std::unordered_map<size_t, std::vector<void *>> g_arena_free;     // size class -> cached blocks
-std::unordered_map<void *, size_t> g_arena_live;                  // block -> size class
+std::unordered_map<size_t, std::vector<void *>> g_arena_free[kMaxDevices];     // size class -> cached blocks
+struct LiveBlock { size_t cls; int device; };
+std::unordered_map<void *, LiveBlock> g_arena_live;                            // block -> size class, owner device
 
 // classes are spaced 12.5 % apart (and at least 512 B), so a block is at most 1/8 larger than requested
 size_t arena_class(size_t bytes) {
@@ -63,26 +79,27 @@ size_t arena_class(size_t bytes) {
 }  // namespace
 
 void *arena_alloc(size_t bytes) {
-    rt();
+    const int dev = rt().device;
     const size_t cls = arena_class(bytes);
     std::lock_guard<std::mutex> lock(g_arena_mutex);
-    auto &bin = g_arena_free[cls];
+    auto &bin = g_arena_free[dev][cls];
     void *p = nullptr;
     if (!bin.empty()) {
         p = bin.back();
         bin.pop_back();
     } else {
+        cudaSetDevice(dev);
         cudaError_t e = cudaMalloc(&p, cls);
-        if (e == cudaErrorMemoryAllocation) {           // give the cache back and retry once
+        if (e == cudaErrorMemoryAllocation) {           // give this device's cache back and retry once
             cudaGetLastError();
-            for (auto &kv : g_arena_free) { for (void *q : kv.second) cudaFree(q); kv.second.clear(); }
+            for (auto &kv : g_arena_free[dev]) { for (void *q : kv.second) cudaFree(q); kv.second.clear(); }
             e = cudaMalloc(&p, cls);
         }
         if (e != cudaSuccess)
             throw Error(e == cudaErrorMemoryAllocation ? GMSB_ERR_OOM : GMSB_ERR_CUDA,
                         std::string("cudaMalloc(") + std::to_string(cls) + " bytes): " + cudaGetErrorString(e));
     }
-    g_arena_live[p] = cls;
+    g_arena_live[p] = LiveBlock{cls, dev};
     return p;
 }
 
@@ -90,14 +107,21 @@ void arena_free(void *p) {
     std::lock_guard<std::mutex> lock(g_arena_mutex);
     auto it = g_arena_live.find(p);
     if (it == g_arena_live.end()) return;
-    g_arena_free[it->second].push_back(p);
+    g_arena_free[it->second.device][it->second.cls].push_back(p);
     g_arena_live.erase(it);
 }
 
 void arena_trim() {
     std::lock_guard<std::mutex> lock(g_arena_mutex);
-    cudaDeviceSynchronize();
-    for (auto &kv : g_arena_free) { for (void *q : kv.second) cudaFree(q); kv.second.clear(); }
+    int prev = 0;
+    cudaGetDevice(&prev);
+    for (int dev = 0; dev < kMaxDevices; ++dev) {
+        if (g_arena_free[dev].empty()) continue;
+        cudaSetDevice(dev);
+        cudaDeviceSynchronize();
+        for (auto &kv : g_arena_free[dev]) { for (void *q : kv.second) cudaFree(q); kv.second.clear(); }
+    }
+    cudaSetDevice(prev);
 }
 
 template <typename F>
@@ -141,18 +165,41 @@ GMSB_API int gmsb_device_count(int *count) {
 
 GMSB_API int gmsb_set_device(int device) {
     return guarded([&] {
-        GMSB_REQUIRE(device >= 0, "negative device index");
+        GMSB_REQUIRE(device >= 0 && device < kMaxDevices, "bad device index");
         g_device = device;
-        if (g_rt_ready) {
-            GMSB_CUDA(cudaSetDevice(device));
-            cudaDeviceProp prop{};
-            GMSB_CUDA(cudaGetDeviceProperties(&prop, device));
-            g_rt.device = device;
-            g_rt.sm_count = prop.multiProcessorCount;
-            g_rt.smem_optin = prop.sharedMemPerBlockOptin;
-        } else {
-            rt();
-        }
+        t_device = -1;
+        GMSB_CUDA(cudaSetDevice(device));
+        rt();
+    });
+}
+
+GMSB_API int gmsb_set_devices(int n, const int *ids) {
+    return guarded([&] {
+        mg_set_devices(n, ids);
+        g_device = ids[0];
+        t_device = -1;
+        GMSB_CUDA(cudaSetDevice(ids[0]));
+        rt();
+    });
+}
+GMSB_API int gmsb_tc_total_multi(gmsb_graph_t g, uint64_t *out) { return guarded([&] { mg_tc_total(G(g), out); }); }
+GMSB_API int gmsb_tc_vertex2_multi(gmsb_graph_t g, int64_t *out_n) {
+    return guarded([&] {
+        Graph &gr = G(g);
+        GMSB_REQUIRE(out_n || gr.n == 0, "null output");
+        mg_tc_vertex2(gr, out_n);
+    });
+}
+GMSB_API int gmsb_kclique_count_multi(gmsb_graph_t g, int k, uint64_t *out) {
+    return guarded([&] {
+        GMSB_REQUIRE(out && k >= 1, "kclique_count: bad arguments");
+        mg_kclique_count(G(g), k, out);
+    });
+}
+GMSB_API int gmsb_edge_similarity_multi(gmsb_graph_t g, int metric, double *out, int64_t *m_out) {
+    return guarded([&] {
+        GMSB_REQUIRE(metric >= 0 && metric <= GMSB_SIM_PREF_ATT, "invalid similarity measure");
+        mg_edge_similarity(G(g), metric, out, m_out);
     });
 }
 
@@ -165,7 +212,12 @@ GMSB_API int gmsb_set_stream(void *s) {
 GMSB_API int gmsb_trim_memory(void) { return guarded([&] { arena_trim(); }); }
 GMSB_API int gmsb_synchronize(void) { return guarded([&] { GMSB_CUDA(cudaStreamSynchronize(rt().stream)); }); }
 GMSB_API int gmsb_launch_count(uint64_t *count) {
-    return guarded([&] { GMSB_REQUIRE(count, "null argument"); *count = g_rt_ready ? g_rt.launches : 0; });
+    return guarded([&] {
+        GMSB_REQUIRE(count, "null argument");
+        uint64_t total = 0;                      // over all devices this process has used
+        for (int d = 0; d < kMaxDevices; ++d) if (g_rt_ready[d]) total += g_rts[d].launches;
+        *count = total;
+    });
 }
 
 // ---- generators (host) -----------------------------------------------------------------------------------------
@@ -267,6 +319,14 @@ GMSB_API int gmsb_order_degeneracy_approx(gmsb_graph_t g, double epsilon, int ra
         Graph &gr = G(g);
         GMSB_REQUIRE(out || gr.n == 0, "null output");
         degeneracy_order_approx(gr, epsilon, rank_format != 0, out);
+    });
+}
+GMSB_API int gmsb_order_degeneracy_approx_ex(gmsb_graph_t g, double epsilon, int rank_format, int boundary, int pull,
+                                             uint64_t seed, int32_t *out) {
+    return guarded([&] {
+        Graph &gr = G(g);
+        GMSB_REQUIRE(out || gr.n == 0, "null output");
+        degeneracy_order_approx_ex(gr, epsilon, rank_format != 0, boundary, pull != 0, seed, out);
     });
 }
 GMSB_API int gmsb_graph_worth_relabelling(gmsb_graph_t g, int *out) {

@@ -43,8 +43,11 @@ struct Runtime {
     int device = -1;
     size_t smem_optin = 0;
 };
-Runtime &rt();             // lazily initialised; throws GMSB_ERR_CUDA when no device is usable
+Runtime &rt();             // of the calling thread's device; lazily initialised; throws GMSB_ERR_CUDA without a device
 void set_last_error(const std::string &msg);
+const std::string &last_error_message();
+int current_device();      // the calling thread's bound device, else the process's primary device
+void bind_device(int device);      // bind the calling host thread to a device (-1: back to the primary one)
 void *arena_alloc(size_t bytes);   // caching device allocator (size-class free lists over cudaMalloc)
 void arena_free(void *p);
 void arena_trim();                 // give every cached block back to the driver
@@ -151,6 +154,8 @@ struct Graph {
     DevBuf<vid_t> nbr;          // slots, ascending within each list
     Dag *dag = nullptr;         // cached degree-oriented DAG (undirected graphs only)
     bool dag_pinned = false;    // the DAG was built with the graph (GMSB_BUILD_ORIENT): reuse_plan = 0 keeps it
+    void *replicas = nullptr;   // copies on the other devices of gmsb_set_devices (mgpu.cu)
+    void (*release_replicas)(void *) = nullptr;
     ~Graph();
 };
 

@@ -491,7 +491,7 @@ __global__ void k_list_degrees(const vid_t *__restrict__ verts, int64_t cnt, con
 // above.  GMSB_KCLIQUE_IMPL=warp|lane forces one family (A/B measurements, tests); the default takes the lane
 // kernels where they are faster (measured on B200) and supported (4 <= k <= 10).
 constexpr int kLaneMinK = 5;
-constexpr int kPairMinDefault = 512;
+constexpr int kPairMinDefault = 128;       // k = 7, scale 20: 85.7 s (512) -> 67.5 s (256) -> 64.5 s (128)
 bool use_lane_kernels(int k) {
     const char *e = std::getenv("GMSB_KCLIQUE_IMPL");
     if (e && !std::strcmp(e, "warp")) return false;

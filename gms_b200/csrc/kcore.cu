@@ -12,6 +12,9 @@
 #include "sort.cuh"
 #include "isect.cuh"
 #include "ops.cuh"
+#include <algorithm>
+#include <cmath>
+#include <vector>
 
 namespace gmsb {
 
@@ -135,6 +138,158 @@ __global__ void k_adg_relax(const eid_t *__restrict__ off, const vid_t *__restri
     }
 }
 }  // namespace
+
+namespace {
+// live[i] for the vertices that are still in the graph, ascending (the reference's vArray after its partition)
+__global__ void k_collect_live(int64_t n, const int *__restrict__ gone, vid_t *__restrict__ live, int *__restrict__ nlive) {
+    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x)
+        if (!gone[v]) live[atomicAdd(nlive, 1)] = (vid_t)v;
+}
+__global__ void k_live_degree_min(int64_t n, const int *__restrict__ deg, const int *__restrict__ gone, int *__restrict__ mn) {
+    int m = 0x7fffffff;
+    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x)
+        if (!gone[v]) m = min(m, deg[v]);
+    for (int o = 16; o; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMin(mn, m);
+}
+__global__ void k_gather_degrees(const vid_t *__restrict__ live, const int *__restrict__ picks, int npick,
+                                 const int *__restrict__ deg, int *__restrict__ out) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npick; i += gridDim.x * blockDim.x) out[i] = deg[live[picks[i]]];
+}
+// PULL-style update (degeneracy_approx_set.h:73-78): every remaining vertex v subtracts |N(v) ∩ X| where X is the set
+// removed in this round — the hot path's intersect_count with one shared right-hand set.  One warp per remaining
+// vertex; X is ascending; galloping when one side is much shorter, else merge path (isect.cuh).
+__global__ void __launch_bounds__(256)
+k_adg_pull(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, const vid_t *__restrict__ live, int nlive,
+           const int *__restrict__ gone, const vid_t *__restrict__ X, int nx, int *__restrict__ deg) {
+    __shared__ vid_t stage[8][kMergeTile + 2];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = warp; i < nlive; i += nwarps) {
+        const vid_t v = live[i];
+        if (gone[v]) continue;                         // removed in this round: it is in X itself
+        const eid_t b = off[v];
+        const int dv = (int)(off[v + 1] - b);
+        if (dv == 0) continue;
+        const int lo = dv < nx ? dv : nx, hi = dv < nx ? nx : dv;
+        unsigned long long c = (long long)hi >= 8ll * lo ? warp_gallop_count(nbr + b, dv, X, nx, lane)
+                                                         : warp_merge_count(nbr + b, dv, X, nx, lane, stage[wib]);
+        c = warp_sum(c);
+        if (lane == 0 && c) deg[v] -= (int)c;
+    }
+}
+__global__ void k_low_ids(const uint64_t *__restrict__ sorted, int qs, vid_t *__restrict__ out) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < qs; i += gridDim.x * blockDim.x) out[i] = (vid_t)(uint32_t)sorted[i];
+}
+inline uint64_t wyrand_next(uint64_t &s) {           // gms/third_party/fast_statistics.h:92-97
+    s += 0xa0761d6478bd642full;
+    __uint128_t t = (__uint128_t)s * (s ^ 0xe7037ed1a0b428dbull);
+    return (uint64_t)(t >> 64) ^ (uint64_t)t;
+}
+}  // namespace
+
+// Replaces  PpParallel::getDegeneracyOrderingApprox{CGraph,SGraph}<boundary, useRankFormat>
+//           gms/algorithms/preprocessing/parallel/degeneracy_approx_csr.h:13-78 (push), degeneracy_approx_set.h:14-85 (pull),
+//           boundary_function.h:15-91 (averageDegree, minDegree, probMinDegree, probMedianDegree)
+// boundary: 0 average, 1 min, 2 sampled min, 3 sampled median.  The two sampled rules draw their vertices with WyRand
+// like the reference, which seeds it from the clock and the OpenMP thread number (not reproducible there); here the
+// stream starts from `seed`, so a call is repeatable.  pull != 0 runs the Set form of the update.
+void degeneracy_order_approx_ex(Graph &g, double epsilon, bool rank_format, int boundary, bool pull, uint64_t seed,
+                                vid_t *out_host) {
+    GMSB_REQUIRE(!g.directed, "order_degeneracy_approx: graph must be undirected");
+    GMSB_REQUIRE(epsilon >= 0, "order_degeneracy_approx: epsilon must be non-negative");
+    GMSB_REQUIRE(boundary >= 0 && boundary <= 3, "order_degeneracy_approx: unknown boundary function");
+    Runtime &r = rt();
+    const int64_t n = g.n;
+    if (n == 0) return;
+    GMSB_REQUIRE(n < (int64_t(1) << 31), "order_degeneracy_approx: too many vertices");
+    DevBuf<int> deg(n), gone(n), qsize(1), nlive(1), mn(1);
+    DevBuf<vid_t> out(n), queue(n), live(n), X(n);
+    DevBuf<uint64_t> keys(n), alt(n);
+    DevBuf<unsigned long long> acc(2);
+    gone.zero();
+    k_init_degrees<<<grid_for(n, 256), 256, 0, r.stream>>>(g.off.p, n, deg.p); launched();
+    uint64_t rng = seed;
+    int64_t done = 0;
+    while (done < n) {
+        acc.zero(); qsize.zero();
+        const int64_t remaining = n - done;
+        const bool need_live = pull || boundary >= 2;
+        int h_live = 0;
+        if (need_live) {
+            nlive.zero();
+            k_collect_live<<<grid_for(n, 256), 256, 0, r.stream>>>(n, gone.p, live.p, nlive.p); launched();
+            h_live = nlive.get(0);
+            // atomics fill the list in arbitrary order: make it ascending (the sampled rules index into it)
+            if (h_live > 1) {
+                size_t bytes = 0;
+                GMSB_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, bytes, live.p, queue.p, h_live, 0, bits_for((uint64_t)n), r.stream));
+                DevBuf<uint8_t> tmp(bytes);
+                GMSB_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, bytes, live.p, queue.p, h_live, 0, bits_for((uint64_t)n), r.stream));
+                GMSB_CUDA(cudaMemcpyAsync(live.p, queue.p, sizeof(vid_t) * (size_t)h_live, cudaMemcpyDeviceToDevice, r.stream));
+                r.launches += 4;
+                GMSB_CUDA(cudaStreamSynchronize(r.stream));
+            }
+        }
+        unsigned int border = 0;
+        if (boundary == 0) {
+            k_live_degree_sum<<<grid_for(n, 256), 256, 0, r.stream>>>(n, deg.p, gone.p, acc.p); launched();
+            unsigned long long h[2];
+            acc.download(h, 2);
+            border = (unsigned int)((1 + epsilon) * ((double)(long long)h[0] / (double)h[1]));     // boundary_function.h:15-25
+        } else if (boundary == 1) {
+            const int big = 0x7fffffff;
+            GMSB_CUDA(cudaMemcpyAsync(mn.p, &big, sizeof(int), cudaMemcpyHostToDevice, r.stream));
+            k_live_degree_min<<<grid_for(n, 256), 256, 0, r.stream>>>(n, deg.p, gone.p, mn.p); launched();
+            border = (unsigned int)(2 * (1 + epsilon) * mn.get(0));                                   // :27-35
+        } else {
+            // :37-91 — size <= 3 special cases, else max(4, size^(0.5 (0.001 + 1 - eps))) draws
+            std::vector<int> picks;
+            const int size = (int)remaining;
+            if (size <= 3) { for (int i = 0; i < size; ++i) picks.push_back(i); }
+            else {
+                const int trials = std::max(4, (int)std::pow((double)size, 0.5 * (0.001 + (1 - epsilon))));
+                for (int i = 0; i < trials; ++i)
+                    picks.push_back((int)(((uint64_t)(uint32_t)wyrand_next(rng) * (uint64_t)(uint32_t)size) >> 32));   // fastrange32
+            }
+            DevBuf<int> dp((size_t)picks.size()), dd((size_t)picks.size());
+            dp.upload(picks.data(), picks.size());
+            k_gather_degrees<<<grid_for((int64_t)picks.size(), 256), 256, 0, r.stream>>>(live.p, dp.p, (int)picks.size(),
+                                                                                        deg.p, dd.p);
+            launched();
+            std::vector<int> draws(picks.size());
+            dd.download(draws.data(), draws.size());
+            std::sort(draws.begin(), draws.end());
+            if (boundary == 2) border = (unsigned int)draws.front();
+            else border = (unsigned int)(size <= 2 ? draws.front() : (size == 3 ? draws[1] : draws[draws.size() / 2]));
+            // the sampled rules may pick a border below every remaining counter's ... no: the border IS some
+            // remaining vertex's counter, so at least that vertex leaves and the loop makes progress
+        }
+        k_collect_keys<<<grid_for(n, 256), 256, 0, r.stream>>>(n, border, deg.p, gone.p, keys.p, qsize.p); launched();
+        const int qs = qsize.get(0);
+        GMSB_REQUIRE(qs > 0, "order_degeneracy_approx: no progress");
+        uint64_t *sorted = radix_sort_keys(keys.p, alt.p, qs, 0, 64);
+        k_adg_assign<<<grid_for(qs, 256), 256, 0, r.stream>>>(sorted, qs, done, rank_format ? 1 : 0, out.p, queue.p);
+        launched();
+        if (!pull) {
+            k_adg_relax<<<grid_for((int64_t)qs * 32, 256), 256, 0, r.stream>>>(g.off.p, g.nbr.p, queue.p, qs, deg.p);
+            launched();
+        } else if (qs < h_live) {
+            // X = this round's batch as an ascending set (Set X(start_index, mid), :59)
+            size_t bytes = 0;
+            GMSB_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, bytes, queue.p, X.p, qs, 0, bits_for((uint64_t)n), r.stream));
+            DevBuf<uint8_t> tmp(bytes);
+            GMSB_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, bytes, queue.p, X.p, qs, 0, bits_for((uint64_t)n), r.stream));
+            r.launches += 4;
+            const int grid = (int)std::min<int64_t>(ceil_div(h_live, 8), (int64_t)r.sm_count * 16);
+            k_adg_pull<<<grid, 256, 0, r.stream>>>(g.off.p, g.nbr.p, live.p, h_live, gone.p, X.p, qs, deg.p); launched();
+            GMSB_CUDA(cudaStreamSynchronize(r.stream));
+        }
+        done += qs;
+    }
+    out.download(out_host, n);
+}
 
 void degeneracy_order_approx(Graph &g, double epsilon, bool rank_format, vid_t *out_host) {
     GMSB_REQUIRE(!g.directed, "order_degeneracy_approx: graph must be undirected");

@@ -602,6 +602,9 @@ Graph *induce_directed(const Graph &g, const vid_t *ranking_host) {
 }
 
 Dag::~Dag() { delete_plan(plan); }
-Graph::~Graph() { delete dag; }
+Graph::~Graph() {
+    if (replicas && release_replicas) release_replicas(replicas);
+    delete dag;
+}
 
 }  // namespace gmsb

@@ -325,7 +325,7 @@ void union_batch(Graph &g, int64_t np, const vid_t *a, const vid_t *b, int64_t *
     set_batch(g, SetOp::Union, "union_batch", np, a, b, out_offsets, out_elems, cap);
 }
 
-static void pair_similarity_device(Graph &g, int metric, int64_t np, const vid_t *da, const vid_t *db, double *out) {
+void pair_similarity_device(Graph &g, int metric, int64_t np, const vid_t *da, const vid_t *db, double *out) {
     Runtime &r = rt();
     DevBuf<double> dout(np);
     DevBuf<int> bad(1);
@@ -344,17 +344,29 @@ void pair_similarity(Graph &g, int metric, int64_t np, const vid_t *a, const vid
     pair_similarity_device(g, metric, np, da.p, db.p, out);
 }
 
+void upper_edge_base(Graph &g, DevBuf<int64_t> &base, int64_t *m_out) {
+    Runtime &r = rt();
+    const int64_t n = g.n;
+    DevBuf<int64_t> cnt(n + 1);
+    base.alloc(n + 1);
+    *m_out = 0;
+    if (n) {
+        k_count_upper<<<grid_for(n, 256), 256, 0, r.stream>>>(g.off.p, g.nbr.p, n, cnt.p); launched();
+        exclusive_sum(cnt.p, base.p, n + 1);
+        *m_out = base.get(n);
+    }
+}
+void emit_upper_pairs(Graph &g, const int64_t *base_dev, vid_t *pa, vid_t *pb) {
+    k_emit_upper<<<grid_for(g.n * 32, 256), 256, 0, rt().stream>>>(g.off.p, g.nbr.p, g.n, base_dev, pa, pb); launched();
+}
+
 void edge_similarity(Graph &g, int metric, double *out, int64_t *m_out) {
     GMSB_REQUIRE(!g.directed, "edge_similarity: graph must be undirected");
     Runtime &r = rt();
     const int64_t n = g.n;
     int64_t m = 0;
-    DevBuf<int64_t> cnt(n + 1), base(n + 1);
-    if (n) {
-        k_count_upper<<<grid_for(n, 256), 256, 0, r.stream>>>(g.off.p, g.nbr.p, n, cnt.p); launched();
-        exclusive_sum(cnt.p, base.p, n + 1);
-        m = base.get(n);
-    }
+    DevBuf<int64_t> base;
+    upper_edge_base(g, base, &m);
     if (m_out) *m_out = m;
     if (!out || m == 0) return;
     if (metric != GMSB_SIM_ADAMIC_ADAR && metric != GMSB_SIM_RESOURCE) {

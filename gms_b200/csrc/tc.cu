@@ -23,6 +23,7 @@
 #include "tc_plan.cuh"
 #include <cooperative_groups.h>
 #include <cstdlib>
+#include <cstring>
 
 namespace gmsb {
 
@@ -153,7 +154,7 @@ __global__ void k_classify(const eid_t *__restrict__ off, const vid_t *__restric
 // Counters -> write cursors; items of the hubs (a slice of the descriptor segment each, with its class boundaries).
 __global__ void k_plan_layout(int64_t n, unsigned long long *__restrict__ cw, const int64_t *__restrict__ nitems,
                               const int64_t *__restrict__ item_base, const int64_t *__restrict__ segbase,
-                              Item *__restrict__ items) {
+                              const int32_t *__restrict__ deal, Item *__restrict__ items) {
     for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x) {
         const int64_t c0 = (int64_t)(cw[3 * v] >> kCntShift), c1 = (int64_t)(cw[3 * v + 1] >> kCntShift),
                       c2 = (int64_t)(cw[3 * v + 2] >> kCntShift);
@@ -169,7 +170,7 @@ __global__ void k_plan_layout(int64_t n, unsigned long long *__restrict__ cw, co
             const int64_t s = j * chunk;                           // first descriptor of the slice, relative to b
             const int64_t c = cnt - s < chunk ? cnt - s : chunk;
             Item it;
-            it.v = (int32_t)v; it.begin = b + s; it.count = (int32_t)c;
+            it.v = (int32_t)v; it.begin = b + s; it.count = (int32_t)c; it.deal = deal[v]; it.pad = 0;
             const int64_t a0 = c0 - s, a1 = c0 + c1 - s;
             it.n0 = (int32_t)(a0 < 0 ? 0 : (a0 > c ? c : a0));
             it.n1 = (int32_t)(a1 < 0 ? 0 : (a1 > c ? c : a1));
@@ -226,19 +227,22 @@ k_plan_scatter(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, con
     if ((threadIdx.x & 31) == 0 && hub_u) atomicAdd(&acc[0], hub_u);
 }
 
-// Order key of an item: window class, then L2 tile of its first suffix (tile-major order keeps the lists that
+// Order key of an item: window class, then the L2 tile its suffixes start in (tile-major order keeps the lists that
 // concurrently running CTAs stream inside the L2), then heaviest vertex first.  Window classes: 0 = NEAR (everything
 // after v, up to n-1, fits the small window: no element can fall outside the bitmap), 1 = small window, 2 = wide.
+// The tile is derived from the slice's position inside v's descriptor segment (descriptors arrive in roughly
+// ascending u), not from the descriptors themselves: their order inside a class depends on the order of the atomics
+// of the scatter pass, and the item order has to be the same on every device that builds this schedule.
 constexpr int kNearWords = kSmallWindowBytes / 4 - 1;
-__global__ void k_item_keys(const Item *__restrict__ items, int64_t cnt, const uint64_t *__restrict__ desc, int64_t n,
-                            int tile_shift, const eid_t *__restrict__ off, const vid_t *__restrict__ nbr,
+__global__ void k_item_keys(const Item *__restrict__ items, int64_t cnt, int64_t n, int64_t ntiles,
+                            const int64_t *__restrict__ nitems, const int64_t *__restrict__ item_base,
+                            const eid_t *__restrict__ off, const vid_t *__restrict__ nbr,
                             uint64_t *__restrict__ keys, unsigned long long *__restrict__ cls_count /* 3 */,
                             int *__restrict__ cls_words /* 3 */) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < cnt; i += (int64_t)gridDim.x * blockDim.x) {
         const Item it = items[i];
-        // a slice that mixes classes has no single u-range: use its longest-suffix part (the bulk of its work)
-        const int64_t d = it.begin + (it.n1 < it.count ? it.n1 : (it.n0 < it.count ? it.n0 : 0));
-        const uint64_t tile = tile_shift > 0 ? (desc[d] >> kLenBits) >> tile_shift : 0;
+        const int64_t k = nitems[it.v], j = i - item_base[it.v];
+        const uint64_t tile = (uint64_t)(j * ntiles / k);
         int words = (int)(((int64_t)nbr[off[it.v + 1] - 1] - it.v + 31) >> 5);
         // a NEAR window starts at the multiple of 32 at or below v + 1 and holds every id up to n - 1
         const int64_t reach_words = ((n - 1 - (((int64_t)it.v + 1) & ~int64_t(31))) >> 5) + 1;
@@ -248,6 +252,22 @@ __global__ void k_item_keys(const Item *__restrict__ items, int64_t cnt, const u
         atomicMax(&cls_words[cls], words);
         keys[i] = ((uint64_t)cls << 62) | ((tile & 0x3fffffffull) << 32) | (uint64_t)(uint32_t)(n - 1 - it.v);
     }
+}
+
+// Multi-device partition.  Hubs are dealt to the devices as whole vertices — the descriptors inside v's segment sit in
+// the order the scatter pass's atomics happened to run in, so a slice of it is not the same set of edges on two
+// devices — in snake order over the hubs sorted by descending work (deterministic; the heaviest hubs alternate).
+__global__ void k_hub_keys(int64_t n, const int64_t *__restrict__ nitems, const unsigned long long *__restrict__ cw,
+                           uint64_t *__restrict__ keys, int *__restrict__ nhubs) {
+    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x) {
+        if (nitems[v] == 0) continue;
+        const unsigned long long work = (cw[3 * v] & kWorkMask) + (cw[3 * v + 1] & kWorkMask) + (cw[3 * v + 2] & kWorkMask);
+        keys[atomicAdd(nhubs, 1)] = ((kWorkMask - (work & kWorkMask)) << 26) | (unsigned long long)v;     // heaviest first
+    }
+}
+__global__ void k_hub_deal(const uint64_t *__restrict__ sorted, int nhubs, int32_t *__restrict__ deal) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nhubs; i += gridDim.x * blockDim.x)
+        deal[sorted[i] & ((1ull << 26) - 1ull)] = i;
 }
 
 // ---- counting kernels ----------------------------------------------------------------------------------------------
@@ -460,7 +480,9 @@ k_tc_bitmap2(const Item *__restrict__ items, int64_t first, int64_t stride, int6
         __syncthreads();                              // ticket visible; previous item's clears done
         const int64_t it = (int64_t)s_item;
         if (it >= count) break;
-        const Item item = items[first + it * stride];                     // plan order: L2 tile, then heaviest
+        const Item item = items[it];                                      // plan order: L2 tile, then heaviest
+        // several devices: whole hubs are dealt out (first = this device, stride = devices), see tc_plan.cuh
+        if (stride > 1 && snake_owner(item.deal, (int)stride) != (int)first) { __syncthreads(); continue; }
         const vid_t v = item.v;
         const eid_t ob = off[v], oe = off[v + 1];
         const uint32_t base = NEAR ? (((uint32_t)v + 1u) & ~31u) : (uint32_t)v + 1u;       // first element of the window
@@ -506,7 +528,9 @@ k_tc_bitmap(const Item *__restrict__ items, int64_t first, int64_t stride, int64
         __syncthreads();                              // ticket visible; previous item's clears done
         const int64_t it = (int64_t)s_item;
         if (it >= count) break;
-        const Item item = items[first + it * stride];                     // plan order: L2 tile, then heaviest
+        const Item item = items[it];                                      // plan order: L2 tile, then heaviest
+        // several devices: whole hubs are dealt out (first = this device, stride = devices), see tc_plan.cuh
+        if (stride > 1 && snake_owner(item.deal, (int)stride) != (int)first) { __syncthreads(); continue; }
         const vid_t v = item.v;
         const eid_t ob = off[v], oe = off[v + 1];
         const uint32_t base = (uint32_t)v + 1u;
@@ -537,9 +561,11 @@ k_tc_gallop(const uint64_t *__restrict__ desc, const vid_t *__restrict__ vs, int
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     uint32_t hits = 0;
-    for (int64_t k = warp; k < count; k += nwarps) {
-        const int64_t i = first + k * stride;
+    for (int64_t i = warp; i < count; i += nwarps) {
         const uint64_t ds = desc[i];
+        // several devices: a light edge belongs to the device its slot number names (the order of the list itself
+        // depends on the atomics of the scatter pass)
+        if (stride > 1 && (int64_t)((ds >> kLenBits) % (uint64_t)stride) != first) continue;
         const vid_t v = vs[i];
         const eid_t ob = off[v];
         hits += warp_gallop_count(nbr + (ds >> kLenBits), (int)(ds & kLenMask), nbr + ob, (int)(off[v + 1] - ob), lane);
@@ -548,26 +574,34 @@ k_tc_gallop(const uint64_t *__restrict__ desc, const vid_t *__restrict__ vs, int
     if (threadIdx.x == 0 && s) atomicAdd(total, s);
 }
 
-// Merge-path kernel: one warp per light edge (isect.cuh: warp_merge_count), lists staged through shared memory.
+// Balanced light pairs, one warp per edge.  BLOCK = false (default): merge path — lists staged through shared memory,
+// every lane walks a share of the merge diagonal; true (gmsb_tc_options.reserved[3] = 1, A/B runs): the block-compare
+// intersection of isect.cuh, which was measured SLOWER (scale 24, every edge forced through this kernel: 1066 ms
+// against 534 ms; light edges of the auto schedule 3.59 against 3.19 ms): its 32-step rotation costs the same for a
+// block of three elements as for a full one, and the light lists are short.
 constexpr int kMergeWarps = 8;
 
+template <bool BLOCK>
 __global__ void __launch_bounds__(kMergeWarps * 32)
 k_tc_merge(const uint64_t *__restrict__ desc, const vid_t *__restrict__ vs, int64_t first, int64_t stride,
            int64_t count, const eid_t *__restrict__ off, const vid_t *__restrict__ nbr,
            unsigned long long *__restrict__ total) {
-    __shared__ vid_t stage[kMergeWarps][kMergeTile + 2];
+    __shared__ vid_t stage[BLOCK ? 1 : kMergeWarps][BLOCK ? 1 : kMergeTile + 2];
     __shared__ unsigned long long red[kMergeWarps];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     uint32_t hits = 0;
-    for (int64_t k = warp; k < count; k += nwarps) {
-        const int64_t i = first + k * stride;
+    for (int64_t i = warp; i < count; i += nwarps) {
         const uint64_t ds = desc[i];
+        if (stride > 1 && (int64_t)((ds >> kLenBits) % (uint64_t)stride) != first) continue;
         const vid_t v = vs[i];
         const eid_t ob = off[v];
-        hits += warp_merge_count(nbr + (ds >> kLenBits), (int)(ds & kLenMask), nbr + ob, (int)(off[v + 1] - ob), lane,
-                                 stage[wib]);
+        if constexpr (BLOCK)
+            hits += warp_block_count(nbr + (ds >> kLenBits), (int)(ds & kLenMask), nbr + ob, (int)(off[v + 1] - ob), lane);
+        else
+            hits += warp_merge_count(nbr + (ds >> kLenBits), (int)(ds & kLenMask), nbr + ob, (int)(off[v + 1] - ob), lane,
+                                     stage[wib]);
     }
     unsigned long long s = block_sum(hits, red);
     if (threadIdx.x == 0 && s) atomicAdd(total, s);
@@ -587,6 +621,7 @@ gmsb_tc_options normalise(const gmsb_tc_options *in) {
 bool same_plan(const gmsb_tc_options &a, const gmsb_tc_options &b) {
     return a.variant == b.variant && a.hub_bitmap_bits == b.hub_bitmap_bits && a.gallop_ratio == b.gallop_ratio &&
            a.hub_min_work == b.hub_min_work && a.reserved[0] == b.reserved[0] && a.reserved[1] == b.reserved[1];
+    // (reserved[2], reserved[3] pick kernel builds, not the schedule)
 }
 
 TcPlan *build_plan(const Dag &d, const gmsb_tc_options &opt) {
@@ -641,12 +676,30 @@ TcPlan *build_plan(const Dag &d, const gmsb_tc_options &opt) {
         p->n_items = item_base.get(n);
         p->items.alloc(p->n_items);
         p->desc.alloc(p->n_bitmap_edges);
-        k_plan_layout<<<grid_for(n, 256), 256, 0, r.stream>>>(n, cw.p, nitems.p, item_base.p, segbase.p, p->items.p);
+        GMSB_REQUIRE(n <= (int64_t(1) << 26), "tc: too many vertices for the hub deal key");
+        DevBuf<int32_t> deal(n);
+        {
+            DevBuf<uint64_t> hk(n), hk2(n);
+            DevBuf<int> nh(1);
+            nh.zero();
+            k_hub_keys<<<grid_for(n, 256), 256, 0, r.stream>>>(n, nitems.p, cw.p, hk.p, nh.p); launched();
+            const int n_hubs = nh.get(0);
+            if (n_hubs) {
+                uint64_t *sorted = radix_sort_keys(hk.p, hk2.p, n_hubs, 0, 64);
+                k_hub_deal<<<grid_for(n_hubs, 256), 256, 0, r.stream>>>(sorted, n_hubs, deal.p); launched();
+            }
+        }
+        k_plan_layout<<<grid_for(n, 256), 256, 0, r.stream>>>(n, cw.p, nitems.p, item_base.p, segbase.p, deal.p,
+                                                             p->items.p);
         launched();
         // both light lists are sized for all light edges; the scatter pass decides merge / gallop per edge
         p->m_desc.alloc(n_light); p->m_v.alloc(n_light); p->g_desc.alloc(n_light); p->g_v.alloc(n_light);
         DevBuf<unsigned long long> cursors(2), hub_u(1);
         cursors.zero(); hub_u.zero();
+        // (A variant that kept the cursors of the last 4096 vertices in shared memory per 2048-vertex tile — one global
+        // ATOM per non-empty counter and tile instead of one per edge — was measured slower at scale 24: 14.8 ms
+        // against 9.4 ms; the two passes over the tile and the 48 KB of shared cursors per CTA cost more than the
+        // returns of the global atomics.)
         k_plan_scatter<G><<<grid_for(n * G, 256), 256, 0, r.stream>>>(
             d.off.p, d.nbr.p, d.dplus.p, n, cw.p, p->desc.p, opt.variant, opt.gallop_ratio, p->m_desc.p, p->m_v.p,
             p->g_desc.p, p->g_v.p, cursors.p, hub_u.p);
@@ -662,11 +715,12 @@ TcPlan *build_plan(const Dag &d, const gmsb_tc_options &opt) {
             DevBuf<uint64_t> ik(p->n_items), ik2(p->n_items);
             DevBuf<Item> items2(p->n_items);
             const int tile_shift = opt.reserved[1] > 0 ? opt.reserved[1] : (opt.reserved[1] < 0 ? 0 : 24);
+            const int64_t ntiles = tile_shift > 0 ? std::max<int64_t>(1, (m + (int64_t(1) << tile_shift) - 1) >> tile_shift) : 1;
             DevBuf<unsigned long long> ccnt(3);
             DevBuf<int> cwords(3);
             ccnt.zero(); cwords.zero();
-            k_item_keys<<<grid_for(p->n_items, 256), 256, 0, r.stream>>>(p->items.p, p->n_items, p->desc.p, n,
-                                                                        tile_shift, d.off.p, d.nbr.p, ik.p, ccnt.p,
+            k_item_keys<<<grid_for(p->n_items, 256), 256, 0, r.stream>>>(p->items.p, p->n_items, n, ntiles, nitems.p,
+                                                                        item_base.p, d.off.p, d.nbr.p, ik.p, ccnt.p,
                                                                         cwords.p);
             launched();
             unsigned long long h_cc[3];
@@ -701,7 +755,8 @@ TcPlan &ensure_plan(Graph &g, const gmsb_tc_options &opt) {
     if (!opt.reuse_plan && !g.dag_pinned) { delete g.dag; g.dag = nullptr; }
     if (!g.dag) g.dag = build_degree_dag(g);
     Dag &d = *g.dag;
-    if (d.plan && !same_plan(d.plan->opt, opt)) { delete_plan(d.plan); d.plan = nullptr; }
+    // reuse_plan == 2: the oriented representation stays (the FromCGraph analogue), the kernel-specific schedule is rebuilt
+    if (d.plan && (opt.reuse_plan == 2 || !same_plan(d.plan->opt, opt))) { delete_plan(d.plan); d.plan = nullptr; }
     if (!d.plan) d.plan = build_plan(d, opt);
     return *d.plan;
 }
@@ -723,9 +778,9 @@ void tc_total(Graph &g, const gmsb_tc_options &opt_in, uint64_t *out, gmsb_tc_st
     DevBuf<unsigned long long> total(1);
     total.zero();
     const int P = opt.part_count, pi = opt.part_index;
-    const int64_t my_items = part_size(p.n_items, pi, P);
-    const int64_t my_merge = part_size(p.n_merge, pi, P);
-    const int64_t my_gallop = part_size(p.n_gallop, pi, P);
+    // every device walks the whole item / light lists and keeps what it owns (whole hubs by deal position, light edges
+    // by slot number): ownership must not depend on the order the scatter pass's atomics ran in
+    const int64_t my_items = p.n_items, my_merge = p.n_merge, my_gallop = p.n_gallop;
 
     t_bm.start();
     if (my_items) {
@@ -734,7 +789,7 @@ void tc_total(Graph &g, const gmsb_tc_options &opt_in, uint64_t *out, gmsb_tc_st
         tickets.zero();
         // one persistent wave per window class (the ticket's free is stream-ordered after the kernels)
         auto launch = [&](auto kern, int BLOCK, const Item *items, int64_t cnt, int cap_words, unsigned int *ticket) {
-            const int64_t mine = part_size(cnt, pi, P);
+            const int64_t mine = cnt;
             if (mine == 0) return;
             const size_t smem = ((size_t)cap_words + 1) * 4;
             if (smem > 48 * 1024)
@@ -775,8 +830,12 @@ void tc_total(Graph &g, const gmsb_tc_options &opt_in, uint64_t *out, gmsb_tc_st
     t_mg.start();
     if (my_merge) {
         int grid = (int)std::min<int64_t>(ceil_div(my_merge, kMergeWarps), (int64_t)r.sm_count * 16);
-        k_tc_merge<<<grid, kMergeWarps * 32, 0, r.stream>>>(p.m_desc.p, p.m_v.p, pi, P, my_merge, d.off.p, d.nbr.p,
-                                                            total.p);
+        if (opt.reserved[3] == 1)
+            k_tc_merge<true><<<grid, kMergeWarps * 32, 0, r.stream>>>(p.m_desc.p, p.m_v.p, pi, P, my_merge, d.off.p,
+                                                                      d.nbr.p, total.p);
+        else
+            k_tc_merge<false><<<grid, kMergeWarps * 32, 0, r.stream>>>(p.m_desc.p, p.m_v.p, pi, P, my_merge, d.off.p,
+                                                                       d.nbr.p, total.p);
         launched();
     }
     t_mg.stop();
@@ -796,8 +855,8 @@ void tc_total(Graph &g, const gmsb_tc_options &opt_in, uint64_t *out, gmsb_tc_st
         s.wedges_checked = p.wedges / P;
         s.oriented_edges = d.m;
         s.edges_bitmap = part_size(p.n_bitmap_edges, pi, P);
-        s.edges_merge = my_merge;
-        s.edges_gallop = my_gallop;
+        s.edges_merge = part_size(p.n_merge, pi, P);          // (shares by count; ownership is by hub / by slot number)
+        s.edges_gallop = part_size(p.n_gallop, pi, P);
         s.ms_orient = t_orient.ms();
         s.ms_bitmap = t_bm.ms();
         s.ms_merge = t_mg.ms();

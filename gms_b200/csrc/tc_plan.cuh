@@ -23,7 +23,15 @@ struct Item {            // one CTA work unit: a slice of hub v's incoming descr
     int32_t count;       // descriptors in the slice
     int32_t n0, n1;      // [0,n0) class 0, [n0,n1) class 1, [n1,count) class 2
     int64_t begin;
+    int32_t deal;        // position of v among the hubs by descending work: multi-device owner = snake(deal, devices)
+    int32_t pad;
 };
+
+// owner of deal position d among P devices: 0 1 .. P-1 P-1 .. 1 0 0 1 ..
+__host__ __device__ inline int snake_owner(int d, int P) {
+    const int r = d % (2 * P);
+    return r < P ? r : 2 * P - 1 - r;
+}
 
 struct TcPlan {
     gmsb_tc_options opt{};

@@ -65,7 +65,8 @@ __device__ __forceinline__ void support_class(const uint64_t *__restrict__ dptr,
 
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
-k_support_bitmap(const Item *__restrict__ items, int64_t count, uint32_t cap_words, int max_dplus,
+k_support_bitmap(const Item *__restrict__ items, int64_t first, int64_t stride, int64_t count, uint32_t cap_words,
+                 int max_dplus,
                  const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, const uint64_t *__restrict__ desc,
                  uint32_t *__restrict__ sup, unsigned int *__restrict__ ticket) {
     extern __shared__ uint32_t smem[];
@@ -83,6 +84,7 @@ k_support_bitmap(const Item *__restrict__ items, int64_t count, uint32_t cap_wor
         const int64_t it = (int64_t)s_item;
         if (it >= count) break;
         const Item item = items[it];
+        if (stride > 1 && snake_owner(item.deal, (int)stride) != (int)first) { __syncthreads(); continue; }
         const vid_t v = item.v;
         const eid_t ob = off[v];
         const int dv = (int)(off[v + 1] - ob);
@@ -109,13 +111,14 @@ k_support_bitmap(const Item *__restrict__ items, int64_t count, uint32_t cap_wor
 
 // Light edges: one warp per edge, lanes binary-search elements of the shorter list in the longer one.
 __global__ void __launch_bounds__(256)
-k_support_light(const uint64_t *__restrict__ desc, const vid_t *__restrict__ vs, int64_t count,
-                const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, uint32_t *__restrict__ sup) {
+k_support_light(const uint64_t *__restrict__ desc, const vid_t *__restrict__ vs, int64_t first, int64_t stride,
+                int64_t count, const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, uint32_t *__restrict__ sup) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t i = warp; i < count; i += nwarps) {
         const uint64_t ds = desc[i];
+        if (stride > 1 && (int64_t)((ds >> kLenBits) % (uint64_t)stride) != first) continue;
         const vid_t v = vs[i];
         const int64_t sa = (int64_t)(ds >> kLenBits), sb = off[v];
         const int na = (int)(ds & kLenMask), nb = (int)(off[v + 1] - sb);
@@ -165,14 +168,14 @@ __global__ void k_unrank(const unsigned long long *__restrict__ t2, const vid_t 
 }
 
 // Score of every undirected edge a<b (CSR order of the ORIGINAL graph) from the support of its oriented copy.
-__global__ void k_edge_scores(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, int64_t n,
+__global__ void k_edge_scores(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, int64_t a_begin, int64_t n,
                               const int64_t *__restrict__ base, const vid_t *__restrict__ rank,
                               const eid_t *__restrict__ doff, const vid_t *__restrict__ dnbr,
                               const uint32_t *__restrict__ sup, int metric, double *__restrict__ out) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t a = warp; a < n; a += nwarps) {
+    for (int64_t a = a_begin + warp; a < n; a += nwarps) {
         const eid_t e1 = off[a + 1];
         const int64_t c = base[a + 1] - base[a];
         const eid_t s0 = e1 - c;
@@ -200,8 +203,10 @@ __global__ void k_edge_scores(const eid_t *__restrict__ off, const vid_t *__rest
 
 }  // namespace
 
-// support of every oriented edge, in the DAG's CSR order (rank space)
-void tc_support(Graph &g, DevBuf<uint32_t> &sup) {
+// support of every oriented edge, in the DAG's CSR order (rank space).  part_index / part_count: this device credits
+// the triangles of its share of the schedule only (items and light edges dealt round-robin as in tc_total); the shares
+// add up to the full support (multi-GPU: one all-reduce, mgpu.cu).
+void tc_support(Graph &g, DevBuf<uint32_t> &sup, int pi, int P) {
     Runtime &r = rt();
     gmsb_tc_options opt = normalise_tc_options(nullptr);
     opt.reuse_plan = 1;
@@ -210,7 +215,8 @@ void tc_support(Graph &g, DevBuf<uint32_t> &sup) {
     sup.alloc(d.m);
     sup.zero();
     if (d.m == 0) return;
-    if (p.n_items) {
+    const int64_t my_items = p.n_items;         // every device walks all items and keeps the hubs it owns
+    if (my_items) {
         constexpr int BLOCK = 512;
         auto kern = k_support_bitmap<BLOCK>;
         const size_t smem = ((size_t)p.max_span_words + 1 + 2 * (size_t)p.max_hub_dplus) * 4;   // only hubs are staged
@@ -220,53 +226,73 @@ void tc_support(Graph &g, DevBuf<uint32_t> &sup) {
         int resident = 0;
         GMSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, BLOCK, smem));
         GMSB_REQUIRE(resident >= 1, "tc_support: kernel does not fit on an SM");
-        const int grid = (int)std::min<int64_t>(p.n_items, (int64_t)r.sm_count * resident);
+        const int grid = (int)std::min<int64_t>(my_items, (int64_t)r.sm_count * resident);
         DevBuf<unsigned int> ticket(1);
         ticket.zero();
-        kern<<<grid, BLOCK, smem, r.stream>>>(p.items.p, p.n_items, (uint32_t)p.max_span_words, p.max_hub_dplus, d.off.p,
-                                              d.nbr.p, p.desc.p, sup.p, ticket.p);
+        kern<<<grid, BLOCK, smem, r.stream>>>(p.items.p, pi, P, my_items, (uint32_t)p.max_span_words, p.max_hub_dplus,
+                                              d.off.p, d.nbr.p, p.desc.p, sup.p, ticket.p);
+        launched();
+        GMSB_CUDA(cudaStreamSynchronize(r.stream));
+    }
+    const int64_t my_merge = p.n_merge, my_gallop = p.n_gallop;
+    if (my_merge) {
+        int grid = (int)std::min<int64_t>(ceil_div(my_merge, 8), (int64_t)r.sm_count * 16);
+        k_support_light<<<grid, 256, 0, r.stream>>>(p.m_desc.p, p.m_v.p, pi, P, my_merge, d.off.p, d.nbr.p, sup.p);
         launched();
     }
-    if (p.n_merge) {
-        int grid = (int)std::min<int64_t>(ceil_div(p.n_merge, 8), (int64_t)r.sm_count * 16);
-        k_support_light<<<grid, 256, 0, r.stream>>>(p.m_desc.p, p.m_v.p, p.n_merge, d.off.p, d.nbr.p, sup.p); launched();
+    if (my_gallop) {
+        int grid = (int)std::min<int64_t>(ceil_div(my_gallop, 8), (int64_t)r.sm_count * 16);
+        k_support_light<<<grid, 256, 0, r.stream>>>(p.g_desc.p, p.g_v.p, pi, P, my_gallop, d.off.p, d.nbr.p, sup.p);
+        launched();
     }
-    if (p.n_gallop) {
-        int grid = (int)std::min<int64_t>(ceil_div(p.n_gallop, 8), (int64_t)r.sm_count * 16);
-        k_support_light<<<grid, 256, 0, r.stream>>>(p.g_desc.p, p.g_v.p, p.n_gallop, d.off.p, d.nbr.p, sup.p); launched();
-    }
+}
+
+// t2[r] += support of the edges at rank-space vertex r (t2 zeroed by the caller); linear in sup
+void support_to_vertex2(Graph &g, const uint32_t *sup, unsigned long long *t2) {
+    Runtime &r = rt();
+    Dag &d = *g.dag;
+    if (d.m == 0) return;
+    k_vertex_out_sum<<<grid_for(g.n * 32, 256), 256, 0, r.stream>>>(d.off.p, g.n, sup, t2); launched();
+    k_vertex_in_sum<<<grid_for(d.m, 256), 256, 0, r.stream>>>(d.nbr.p, d.m, sup, t2); launched();
+}
+void vertex2_unrank(Graph &g, const unsigned long long *t2, int64_t *out_dev) {
+    Runtime &r = rt();
+    k_unrank<<<grid_for(g.n, 256), 256, 0, r.stream>>>(t2, g.dag->order.p, g.n, out_dev); launched();
 }
 
 void tc_vertex2(Graph &g, int64_t *out_n) {
     GMSB_REQUIRE(!g.directed, "vertex_count2: graph must be undirected");
-    Runtime &r = rt();
     const int64_t n = g.n;
     if (n == 0) return;
     DevBuf<uint32_t> sup;
     tc_support(g, sup);
-    Dag &d = *g.dag;
     DevBuf<unsigned long long> t2(n);
     DevBuf<int64_t> out(n);
     t2.zero();
-    if (d.m) {
-        k_vertex_out_sum<<<grid_for(n * 32, 256), 256, 0, r.stream>>>(d.off.p, n, sup.p, t2.p); launched();
-        k_vertex_in_sum<<<grid_for(d.m, 256), 256, 0, r.stream>>>(d.nbr.p, d.m, sup.p, t2.p); launched();
-    }
-    k_unrank<<<grid_for(n, 256), 256, 0, r.stream>>>(t2.p, d.order.p, n, out.p); launched();
+    support_to_vertex2(g, sup.p, t2.p);
+    vertex2_unrank(g, t2.p, out.p);
     out.download(out_n, n);
+}
+
+// scores of the undirected edges a<b owned by the vertices [a_begin, a_end) from a complete support array
+void edge_scores_range(Graph &g, int metric, const int64_t *base_dev, const uint32_t *sup, int64_t a_begin, int64_t a_end,
+                       double *out_dev) {
+    Runtime &r = rt();
+    Dag &d = *g.dag;
+    if (a_end <= a_begin) return;
+    k_edge_scores<<<grid_for((a_end - a_begin) * 32, 256), 256, 0, r.stream>>>(g.off.p, g.nbr.p, a_begin, a_end, base_dev,
+                                                                             d.rank.p, d.off.p, d.nbr.p, sup, metric,
+                                                                             out_dev);
+    launched();
 }
 
 // edge_similarity for the metrics that depend on the graph only through the common-neighbour count.
 // `base` = exclusive scan of the per-vertex count of neighbours > vertex (setops.cu builds it).
 void edge_scores_from_support(Graph &g, int metric, const int64_t *base_dev, double *out_dev) {
-    Runtime &r = rt();
     DevBuf<uint32_t> sup;
     tc_support(g, sup);
-    Dag &d = *g.dag;
-    k_edge_scores<<<grid_for(g.n * 32, 256), 256, 0, r.stream>>>(g.off.p, g.nbr.p, g.n, base_dev, d.rank.p, d.off.p,
-                                                                 d.nbr.p, sup.p, metric, out_dev);
-    launched();
-    GMSB_CUDA(cudaStreamSynchronize(r.stream));
+    edge_scores_range(g, metric, base_dev, sup.p, 0, g.n, out_dev);
+    GMSB_CUDA(cudaStreamSynchronize(rt().stream));
 }
 
 }  // namespace gmsb

@@ -9,6 +9,7 @@
 #pragma once
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <iostream>
 #include <stdexcept>
 #include <string>
@@ -223,10 +224,32 @@ private:
     }
 };
 
+// ---- several GPUs in one process -----------------------------------------------------------------------------------
+// UseDevices({0,1,...,7}) once (or the environment variable GMSB_DEVICES="0,1,2,3", read by UseDevicesFromEnv): the
+// entry points below then spread every call over those devices (gmsb_*_multi: CSR replicated over NVLink, partitioned
+// kernels, NCCL all-reduce for array results).  Handles live on the first listed device.
+inline int &multi_device_count() { static int n = 0; return n; }
+inline void UseDevices(const std::vector<int> &ids) {
+    check(gmsb_set_devices(static_cast<int>(ids.size()), ids.data()));
+    multi_device_count() = static_cast<int>(ids.size());
+}
+inline bool UseDevicesFromEnv() {
+    const char *e = std::getenv("GMSB_DEVICES");
+    if (!e || !*e) return false;
+    std::vector<int> ids;
+    for (const char *p = e; *p;) {
+        ids.push_back(std::atoi(p));
+        while (*p && *p != ',') ++p;
+        if (*p == ',') ++p;
+    }
+    UseDevices(ids);
+    return true;
+}
+
 // ---- algorithm entry points, plain names (gms_api.hpp maps the reference's names onto these) ---------------------
 inline size_t count_total(const CudaSetGraph &g) {
     uint64_t t = 0;
-    check(gmsb_tc_total(g.handle(), &t));
+    check(multi_device_count() > 1 ? gmsb_tc_total_multi(g.handle(), &t) : gmsb_tc_total(g.handle(), &t));
     return static_cast<size_t>(t);
 }
 template <class Output = std::vector<int64_t>>
@@ -234,7 +257,7 @@ inline void vertex_count2(const CudaSetGraph &g, Output &counts) {
     const int64_t n = g.num_nodes();
     counts.resize(n);
     std::vector<int64_t> tmp(static_cast<size_t>(std::max<int64_t>(n, 1)));
-    check(gmsb_tc_vertex2(g.handle(), tmp.data()));
+    check(multi_device_count() > 1 ? gmsb_tc_vertex2_multi(g.handle(), tmp.data()) : gmsb_tc_vertex2(g.handle(), tmp.data()));
     for (int64_t i = 0; i < n; ++i) counts[i] = tmp[i];
 }
 template <bool useRankFormat = false, class Output = std::vector<NodeId>>
@@ -276,7 +299,8 @@ inline CudaSetGraph induce_directed_graph(const CudaSetGraph &g, const std::vect
 }
 inline unsigned long long kclique_count(const CudaSetGraph &g, int clique_size) {
     uint64_t c = 0;
-    check(gmsb_kclique_count(g.handle(), clique_size, &c));
+    check(multi_device_count() > 1 ? gmsb_kclique_count_multi(g.handle(), clique_size, &c)
+                                   : gmsb_kclique_count(g.handle(), clique_size, &c));
     return c;
 }
 inline size_t kclique_count_ordered(const CudaSetGraph &g, size_t k) {
@@ -295,9 +319,11 @@ inline std::vector<double> pair_similarity(Metric m, const CudaSetGraph &g, cons
 // one score per undirected edge u<v in CSR order
 inline std::vector<double> edge_similarity(Metric m, const CudaSetGraph &g) {
     int64_t cnt = 0;
+    const bool multi = multi_device_count() > 1;
     check(gmsb_edge_similarity(g.handle(), static_cast<int>(m), nullptr, &cnt));
     std::vector<double> out(static_cast<size_t>(cnt));
-    if (cnt) check(gmsb_edge_similarity(g.handle(), static_cast<int>(m), out.data(), &cnt));
+    if (cnt) check(multi ? gmsb_edge_similarity_multi(g.handle(), static_cast<int>(m), out.data(), &cnt)
+                         : gmsb_edge_similarity(g.handle(), static_cast<int>(m), out.data(), &cnt));
     return out;
 }
 

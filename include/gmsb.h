@@ -12,8 +12,9 @@
  *   - handles are opaque; all array arguments are HOST pointers owned by the caller unless the name ends in
  *     `_device` (then they are device pointers on the current device);
  *   - vertex ids are int32 (gms/common/types.h:9), offsets int64, counts uint64 / int64 as in the reference;
- *   - one host thread per handle at a time; the library works on one CUDA device per process
- *     (gmsb_set_device) and launches on the stream given by gmsb_set_stream (default: the legacy stream 0);
+ *   - one host thread per handle at a time; handles live on the process's primary device (gmsb_set_device) and the
+ *     library launches on the stream given by gmsb_set_stream (default: the legacy stream 0); the *_multi entry
+ *     points spread one call over the devices of gmsb_set_devices;
  *   - there is NO CPU fallback: without a usable CUDA device every compute entry point fails with
  *     GMSB_ERR_CUDA.
  */
@@ -54,6 +55,19 @@ GMSB_API int gmsb_synchronize(void);
 GMSB_API int gmsb_trim_memory(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 GMSB_API int gmsb_launch_count(uint64_t *count);
+
+/* ---- several GPUs in one process ------------------------------------------------------------------------------ */
+/* gmsb_set_devices(n, ids): the devices the *_multi entry points below work on; ids[0] becomes the process's primary
+ * device, where graph handles live.  The handle's CSR is replicated to the other devices over NVLink on first use
+ * (cached), one host thread per device runs the partitioned kernels, scalar counts are summed on the host and array
+ * results go through NCCL (libnccl.so.2, loaded on first use): vertex_count2 is one ncclAllReduce(int64[n]), the
+ * per-edge similarity one ncclAllReduce(uint32[m]) of the edge supports followed by edge-partitioned scoring
+ * (SURVEY.md 8e).  Same results as the single-device entry points. */
+GMSB_API int gmsb_set_devices(int n, const int *ids);
+GMSB_API int gmsb_tc_total_multi(gmsb_graph_t g, uint64_t *out);
+GMSB_API int gmsb_tc_vertex2_multi(gmsb_graph_t g, int64_t *out_n);
+GMSB_API int gmsb_kclique_count_multi(gmsb_graph_t g, int k, uint64_t *out);
+GMSB_API int gmsb_edge_similarity_multi(gmsb_graph_t g, int metric, double *out, int64_t *m_out);
 
 /* ---- synthetic inputs (host side; input preparation, never timed) ---------------------------------------------- */
 /* Generator::MakeRMatEL + PermuteIDs                    gms/third_party/gapbs/generator.h:81-114,52-62
@@ -105,6 +119,15 @@ GMSB_API int gmsb_order_degeneracy(gmsb_graph_t g, int32_t *out_rank);
  * rounds remove every vertex with residual degree <= (1+eps)*average; inside a round vertices are ordered by that
  * degree (ties by id; unspecified in the reference). Ascending convention: first removed = position / rank 0. */
 GMSB_API int gmsb_order_degeneracy_approx(gmsb_graph_t g, double epsilon, int rank_format, int32_t *out);
+/* getDegeneracyOrderingApprox{CGraph,SGraph}<boundary, useRankFormat>
+ *                                                       degeneracy_approx_csr.h:13-78 (push), degeneracy_approx_set.h:14-85 (pull)
+ * boundary = one of boundary_function::{averageDegree, minDegree, probMinDegree, probMedianDegree}
+ * (boundary_function.h:15-91).  pull = 1 is the Set form: every remaining vertex subtracts |N(v) ∩ X|, X the set removed
+ * in the round, one intersect_count per vertex against the shared set X.  Push and pull give the same order.  The two
+ * sampled rules draw with WyRand from `seed` (the reference seeds from the clock: not reproducible there). */
+typedef enum { GMSB_ADG_AVERAGE = 0, GMSB_ADG_MIN = 1, GMSB_ADG_PROB_MIN = 2, GMSB_ADG_PROB_MEDIAN = 3 } gmsb_adg_boundary;
+GMSB_API int gmsb_order_degeneracy_approx_ex(gmsb_graph_t g, double epsilon, int rank_format, int boundary, int pull,
+                                             uint64_t seed, int32_t *out);
 /* WorthRelabelling(g): the CLI's auto-relabel heuristic    gms/third_party/gapbs/benchmark.h:158-176, cli/cli.h:174-181
  * (average degree >= 10 and mean/1.3 > median over 1000 mt19937-sampled non-isolated vertices). */
 GMSB_API int gmsb_graph_worth_relabelling(gmsb_graph_t g, int *out);
@@ -125,7 +148,9 @@ typedef struct {
     int32_t variant;         /* gmsb_tc_variant */
     int32_t part_index;      /* this process handles share part_index of part_count of the oriented edges   */
     int32_t part_count;      /* (multi-GPU: edge partition balanced by work, CSR replicated); 0 or 1 = all    */
-    int32_t reuse_plan;      /* 1: keep the oriented DAG + schedule cached on the handle between calls        */
+    int32_t reuse_plan;      /* 0: build the oriented DAG and the schedule for this call and drop them; 1: keep
+                                both cached on the handle between calls; 2: keep the DAG (the FromCGraph analogue),
+                                rebuild the kernel-specific schedule on every call                             */
     int32_t hub_bitmap_bits; /* bitmap kernel's shared-memory window in bits; 0 = default                     */
     int32_t gallop_ratio;    /* galloping when longer/shorter >= ratio; 0 = default                           */
     int64_t hub_min_work;    /* a vertex is a hub when its incoming wedge work >= this; 0 = default            */

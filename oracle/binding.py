@@ -176,6 +176,7 @@ class CpuLib:
                 "check_degeneracy_rank": (C.c_int64, [C.c_void_p, _i32p]),
                 "core_number_of_rank": (C.c_int64, [C.c_void_p, _i32p]),
                 "adg_order": (None, [C.c_void_p, C.c_double, C.c_int, _i32p, _i32p]),
+                "adg_order_ex": (None, [C.c_void_p, C.c_double, C.c_int, C.c_int, _i32p, _i32p]),
                 "clique_counts_pivot": (None, [C.c_void_p, C.c_int, np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")]),
                 "tc_bytes": (None, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                     C.POINTER(C.c_int64)]),
@@ -184,6 +185,7 @@ class CpuLib:
         else:
             sig.update({"degeneracy_danisch_heap": (None, [C.c_void_p, _i32p]),
                         "adg_order": (None, [C.c_void_p, C.c_double, C.c_int, _i32p]),
+                        "adg_order_ex": (None, [C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int, _i32p]),
                         "load_file": (C.c_void_p, [C.c_char_p, C.c_int]),
                         "write_file": (None, [C.c_void_p, C.c_char_p, C.c_int])})
         self._fn = {}
@@ -287,6 +289,17 @@ class CpuLib:
             self._f("adg_order")(g.h, float(eps), int(rank_format), out, rounds)
             return out[:g.n], rounds[:g.n]
         self._f("adg_order")(g.h, float(eps), int(rank_format), out)
+        return out[:g.n]
+
+    def adg_order_ex(self, g, eps=1.0, rank_format=False, boundary="average", pull=False):
+        """ADG with a boundary function ("average" | "min"); the reference also takes pull=True (the Set form)."""
+        kind = {"average": 0, "min": 1}[boundary]
+        out = np.zeros(max(g.n, 1), np.int32)
+        if self.prefix == "orc_":
+            rounds = np.zeros(max(g.n, 1), np.int32)
+            self._f("adg_order_ex")(g.h, float(eps), int(rank_format), kind, out, rounds)
+            return out[:g.n], rounds[:g.n]
+        self._f("adg_order_ex")(g.h, float(eps), int(rank_format), kind, int(pull), out)
         return out[:g.n]
 
     def clique_counts_pivot(self, dag, kmax):

@@ -7,6 +7,7 @@
 // (Verify::total_count, Verify::vertex_count<2>), which therefore check the GPU results at run time.
 //
 //   oracle/_ref/dropin_tc -g kronecker 16 --deg 16 -n 3 -v
+//   GMSB_DEVICES=0,1,2,3,4,5,6,7 oracle/_ref/dropin_tc -g kronecker 20 --deg 16 -n 3 -v      (one process, eight GPUs)
 #include <gms/third_party/gapbs/benchmark.h>
 #include <gms/common/cli/cli.h>
 #include <gms/representations/graphs/set_graph.h>
@@ -23,6 +24,7 @@ using GMS::BenchmarkKernelBk;
 using gms_b200::CudaSetGraph;
 
 int main(int argc, char *argv[]) {
+    if (gms_b200::UseDevicesFromEnv()) std::cout << "gms-b200: " << gms_b200::multi_device_count() << " devices" << std::endl;
     auto loaded = GMS::CLI::Parser().parse_and_load(argc, argv);
     GMS::CLI::Args &args = std::get<0>(loaded);
     CSRGraph &host_graph = std::get<1>(loaded);

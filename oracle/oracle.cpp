@@ -597,7 +597,8 @@ int64_t orc_check_degeneracy_rank(void *h, const int32_t *rank) { return check_d
 // mean counter of the remaining), ordered inside the round by that counter (the reference's parallel partition + sort
 // leave ties unspecified; here ties go by id), then decrements the counter of EVERY neighbour (push style).
 // round_of (optional) receives the round in which each vertex left, for batch-level comparison with the reference.
-void orc_adg_order(void *h, double eps, int rank_format, int32_t *out, int32_t *round_of) {
+// boundary: 0 = averageDegree (boundary_function.h:15-25), 1 = minDegree (:27-35)
+void orc_adg_order_ex(void *h, double eps, int rank_format, int boundary, int32_t *out, int32_t *round_of) {
     const Graph &g = *G(h);
     const int64_t n = g.n;
     std::vector<int> cnt(n);
@@ -606,9 +607,16 @@ void orc_adg_order(void *h, double eps, int rank_format, int32_t *out, int32_t *
     int64_t done = 0;
     int32_t round = 0;
     while (done < n) {
-        double res = 0;
-        for (vid v : live) res += cnt[v];
-        unsigned int border = (unsigned int)((1 + eps) * (res / (double)live.size()));
+        unsigned int border;
+        if (boundary == 0) {
+            double res = 0;
+            for (vid v : live) res += cnt[v];
+            border = (unsigned int)((1 + eps) * (res / (double)live.size()));
+        } else {
+            int mn = 0x7fffffff;
+            for (vid v : live) mn = std::min(mn, cnt[v]);
+            border = (unsigned int)(2 * (1 + eps) * mn);
+        }
         std::vector<vid> batch, rest;
         for (vid v : live) ((long long)cnt[v] <= (long long)border ? batch : rest).push_back(v);
         std::sort(batch.begin(), batch.end(), [&](vid a, vid b) { return cnt[a] < cnt[b] || (cnt[a] == cnt[b] && a < b); });
@@ -623,6 +631,10 @@ void orc_adg_order(void *h, double eps, int rank_format, int32_t *out, int32_t *
         live.swap(rest);
         ++round;
     }
+}
+
+void orc_adg_order(void *h, double eps, int rank_format, int32_t *out, int32_t *round_of) {
+    orc_adg_order_ex(h, eps, rank_format, 0, out, round_of);
 }
 
 // The reference's own acceptance test for a degeneracy order (verifiers/degeneracy_verifier.h:69-85), in rank

@@ -296,6 +296,31 @@ void gmsref_adg_order(void *h, double eps, int rank_format, int32_t *out) {
         PpParallel::getDegeneracyOrderingApproxCGraph<PpParallel::boundary_function::averageDegree, false>(g, res, eps);
     std::memcpy(out, res.data(), sizeof(NodeId) * res.size());
 }
+// boundary: 0 averageDegree, 1 minDegree; pull: 0 = the CSR (push) form, 1 = the Set (pull) form over SortedSetGraph
+void gmsref_adg_order_ex(void *h, double eps, int rank_format, int boundary, int pull, int32_t *out) {
+    namespace bf = PpParallel::boundary_function;
+    const CSRGraph &g = static_cast<RefGraph *>(h)->g;
+    std::vector<NodeId> res;
+    if (!pull) {
+        if (boundary == 0) {
+            if (rank_format) PpParallel::getDegeneracyOrderingApproxCGraph<bf::averageDegree, true>(g, res, eps);
+            else PpParallel::getDegeneracyOrderingApproxCGraph<bf::averageDegree, false>(g, res, eps);
+        } else {
+            if (rank_format) PpParallel::getDegeneracyOrderingApproxCGraph<bf::minDegree, true>(g, res, eps);
+            else PpParallel::getDegeneracyOrderingApproxCGraph<bf::minDegree, false>(g, res, eps);
+        }
+    } else {
+        SortedSetGraph sg = SortedSetGraph::FromCGraph(g);
+        if (boundary == 0) {
+            if (rank_format) PpParallel::getDegeneracyOrderingApproxSGraph<bf::averageDegree, true, SortedSetGraph>(sg, res, eps);
+            else PpParallel::getDegeneracyOrderingApproxSGraph<bf::averageDegree, false, SortedSetGraph>(sg, res, eps);
+        } else {
+            if (rank_format) PpParallel::getDegeneracyOrderingApproxSGraph<bf::minDegree, true, SortedSetGraph>(sg, res, eps);
+            else PpParallel::getDegeneracyOrderingApproxSGraph<bf::minDegree, false, SortedSetGraph>(sg, res, eps);
+        }
+    }
+    std::memcpy(out, res.data(), sizeof(NodeId) * res.size());
+}
 void *gmsref_induce_directed(void *h, const int32_t *ranking) {
     Quiet q;
     const CSRGraph &g = static_cast<RefGraph *>(h)->g;

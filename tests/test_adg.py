@@ -38,6 +38,51 @@ def test_oracle_adg_matches_reference_rounds(orc, ref, seed):
         assert later <= (2 + 2 * eps) * max(degen, 1) + 1
 
 
+@pytest.mark.parametrize("seed", range(3))
+def test_oracle_adg_boundaries_and_pull_match_reference_rounds(orc, ref, seed):
+    """minDegree boundary and the Set (pull) form of the reference (degeneracy_approx_set.h) against the oracle: the same
+    vertices leave in the same round; push and pull are the same algorithm on the counters of the remaining vertices."""
+    n, m = [(80, 500), (600, 9000), (2500, 30000)][seed]
+    s, d = random_graph_edges(70 + seed, n, m, skew=(seed % 2) * 1.0)
+    go, gr = orc.from_el(s, d, True), ref.from_el(s, d, True)
+    for boundary in ("average", "min"):
+        for eps in (0.0, 0.5):
+            order_o, round_of = orc.adg_order_ex(go, eps, False, boundary)
+            for pull in (False, True):
+                order_r = ref.adg_order_ex(gr, eps, False, boundary, pull)
+                assert sorted(order_r.tolist()) == list(range(go.n))
+                rr = round_of[order_r]
+                assert (np.diff(rr) >= 0).all(), (boundary, eps, pull)
+                assert (np.bincount(rr) == np.bincount(round_of[order_o])).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(3))
+def test_gpu_adg_boundaries_and_pull(gms, orc, seed):
+    n, m = [(80, 500), (600, 9000), (30000, 400000)][seed]
+    s, d = random_graph_edges(80 + seed, n, m, skew=(seed % 2) * 1.0)
+    g, o = gms.Graph.from_edgelist(s, d, True), orc.from_el(s, d, True)
+    degen = orc.check_degeneracy_rank(o, orc.degeneracy_rank(o))
+    for boundary in ("average", "min"):
+        for eps in (0.0, 0.5):
+            want, _ = orc.adg_order_ex(o, eps, False, boundary)
+            for pull in (False, True):       # the Set form subtracts |N(v) ∩ X| per remaining vertex: same order
+                assert (g.degeneracy_order_approx_ex(eps, False, boundary, pull) == want).all(), (boundary, eps, pull)
+            rank = g.degeneracy_order_approx_ex(eps, True, boundary, True)
+            assert (rank[want] == np.arange(o.n)).all()
+    # the sampled boundary functions: a permutation, repeatable for a seed, and a usable orientation for the clique
+    # pipeline (counts do not depend on the order)
+    want4 = o.induce_directed(o.degree_order(True)).kclique(4)
+    for boundary in ("prob_min", "prob_median"):
+        a = g.degeneracy_order_approx_ex(0.1, True, boundary, True, seed=7)
+        b = g.degeneracy_order_approx_ex(0.1, True, boundary, True, seed=7)
+        assert (a == b).all() and sorted(a.tolist()) == list(range(o.n))
+        assert g.orient(a).kclique_count(4) == want4
+        if boundary == "prob_min":          # removing the sampled minimum and everything below it keeps d+ near the degeneracy
+            later = orc.core_number_of_rank(o, (o.n - 1 - a).astype(np.int32))
+            assert later <= 4 * max(degen, 1) + 4
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("seed", range(4))
 def test_gpu_adg_matches_oracle(gms, orc, seed):

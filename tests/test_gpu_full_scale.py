@@ -58,3 +58,15 @@ def test_sampled_edges_against_oracle_at_scale_24(kron24, orc):
     ha, hb = np.meshgrid(hubs, hubs)
     ha, hb = ha.ravel().astype(np.int32), hb.ravel().astype(np.int32)
     assert (g.intersect_count_batch(ha, hb) == o.pair_similarity("comm_neigh", ha, hb).astype(np.uint64)).all()
+
+
+def test_skewed_rmat_scale_20_families_agree(gms):
+    """R-MAT a = 0.65 at scale 20 (max d+ near a thousand, much heavier hubs than the kronecker constants give): the bitmap schedule, the
+    all-gallop schedule, the partition sums and the per-vertex counts agree."""
+    s, d = gms.generate_rmat(20, a=0.65, b=0.15, c=0.15)
+    g = gms.Graph.from_edgelist(s, d, True)
+    auto, st = g.tc_total_ex(reuse_plan=True)
+    assert st["edges_bitmap"] > 0 and st["max_dplus"] > 500
+    assert g.tc_total_ex(variant="gallop")[0] == auto
+    assert sum(g.tc_total_ex(part_index=p, part_count=3, reuse_plan=True)[0] for p in range(3)) == auto
+    assert int(g.tc_vertex2().sum()) == 6 * auto

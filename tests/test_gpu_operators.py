@@ -109,3 +109,24 @@ def test_vertex_counts_properties_at_scale_18(gms):
     # relabelling permutes the per-vertex output
     rel = g.relabel_by_degree()
     assert sorted(rel.tc_vertex2().tolist()) == sorted(v2.tolist())
+
+
+def test_several_gpus_in_one_process(gms):
+    """gmsb_set_devices + the *_multi entry points (mgpu.cu): every visible device (one is enough to exercise the
+    replication / worker-thread / NCCL path; the 2- and 8-GPU runs are recorded under profiles/)."""
+    ids = list(range(min(gms.device_count(), 8)))
+    s, d = gms.generate_rmat(16)
+    gms.set_devices(ids)
+    try:
+        g = gms.Graph.from_edgelist(s, d, True)
+        assert g.tc_total_multi() == 15656287                              # SURVEY.md 8c
+        assert g.kclique_count_multi(4) == 291383976 and g.kclique_count_multi(5) == 4609989471
+        assert (g.tc_vertex2_multi() == g.tc_vertex2()).all()
+        for metric in ("jaccard", "comm_neigh", "resource"):
+            a, b = g.edge_similarity_multi(metric), g.edge_similarity(metric)
+            assert a.tobytes() == b.tobytes(), metric
+        aa, ab = g.edge_similarity_multi("adamic_adar"), g.edge_similarity("adamic_adar")
+        assert a.shape == b.shape and np.allclose(aa, ab, rtol=1e-13, atol=0, equal_nan=True)
+    finally:
+        gms.set_devices([0])
+        gms.set_device(0)

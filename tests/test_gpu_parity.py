@@ -256,3 +256,43 @@ def test_orientation_fallback_path(gms, orc, monkeypatch):
         rank = o.degree_order(True)
         dag, odag = g.orient(rank), o.induce_directed(rank)
         assert same_csr(dag.export_csr(), odag.csr()), cap
+
+
+@pytest.mark.parametrize("scale", [14, 16])
+def test_skewed_rmat_against_the_oracle(gms, orc, scale):
+    """BASELINE.json configs[4]: R-MAT with a = 0.65 (b = c = 0.15): much heavier hubs than the reference's kronecker.
+    Every kernel family against the oracle's count, per-vertex counts, and k-cliques on the same graph."""
+    s, d = gms.generate_rmat(scale, a=0.65, b=0.15, c=0.15)
+    g, o = gms.Graph.from_edgelist(s, d, True), orc.from_el(s, d, True)
+    want = o.tc_total()
+    for v in ("auto", "merge", "gallop", "bitmap"):
+        c, st = g.tc_total_ex(variant=v)
+        assert c == want, (scale, v)
+    bt, _, mx = orc.tc_bytes(o)
+    c, st = g.tc_total_ex()
+    assert st["algorithmic_bytes"] == bt and st["max_dplus"] == mx
+    assert (g.tc_vertex2() == o.tc_vertex2()).all()
+    assert g.tc_total_ex(hub_bitmap_bits=4096, hub_min_work=1)[0] == want      # narrow windows: hubs fall to the light path
+    if scale == 14:
+        dag = o.induce_directed(o.degree_order(True))
+        for k in (4, 5):
+            assert g.kclique_count(k) == dag.kclique(k), k
+    off, nbr = g.export_csr()
+    gp = gms.Graph.from_csr(off, nbr, orient=True)
+    assert gp.tc_total_ex(reuse_plan=False)[0] == want
+
+
+def test_partition_is_consistent_across_independently_built_schedules(gms):
+    """Multi-GPU runs build the schedule once per device; the descriptors inside a hub's segment sit in the order the
+    scatter pass's atomics ran in, so ownership must not depend on it: shares taken from DIFFERENT builds of the
+    schedule have to add up (this is what goes wrong first when the partition leans on a nondeterministic order)."""
+    s, d = gms.generate_rmat(18)
+    graphs = [gms.Graph.from_edgelist(s, d, True) for _ in range(4)]
+    want = 82728031                                                        # SURVEY.md 8c, kronecker-18
+    for variant in ("auto", "bitmap", "gallop"):
+        for parts in (2, 4):
+            got = sum(graphs[p].tc_total_ex(variant=variant, part_index=p, part_count=parts)[0] for p in range(parts))
+            assert got == want, (variant, parts)
+    # per-vertex counts over shares from different builds (mgpu.cu path is covered in test_gpu_operators.py)
+    got = sum(graphs[p].tc_total_ex(part_index=p, part_count=3, reuse_plan=2)[0] for p in range(3))
+    assert got == want

@@ -1,0 +1,9 @@
+set -x
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2g_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2g_pytest.log
+tail -5 gpurun_out/r2g_pytest.log
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 5 --warmup 3 --kclique '4,5' > gpurun_out/r2g_bench_2gpu.json 2> gpurun_out/r2g_bench_2gpu.err; tail -3 gpurun_out/r2g_bench_2gpu.err
+cut -c1-700 gpurun_out/r2g_bench_2gpu.json
+GMSB_DEVICES=0,1 timeout 300 oracle/_ref/dropin_tc -g kronecker 18 --deg 16 -n 2 -v > gpurun_out/r2g_dropin_2gpu.log 2>&1; grep "@@@\|devices" gpurun_out/r2g_dropin_2gpu.log
+timeout 300 python bench.py --steps 5 --warmup 3 --kclique '' --no-cpu-baseline > gpurun_out/r2g_bench_1gpu.json 2> gpurun_out/r2g_bench_1gpu.err
+cut -c1-400 gpurun_out/r2g_bench_1gpu.json
