@@ -411,9 +411,8 @@ def run_ours(args):
     count_ms = float(np.mean(ms_count))
     sched_ms = float(np.mean(ms_sched))
     alg_bytes = st["bytes_bitmap"] / max(world, 1)
-    # (wedges_bitmap / bitmap_items are whole-graph figures, edges_bitmap is this rank's share)
-    min_traffic = 4.0 * st["wedges_bitmap"] / max(world, 1) + 8.0 * st["edges_bitmap"] + \
-        32.0 * st["bitmap_items"] / max(world, 1)
+    # (wedges_bitmap is a whole-graph figure; edges_bitmap / bitmap_items are this rank's share of the schedule)
+    min_traffic = 4.0 * st["wedges_bitmap"] / max(world, 1) + 8.0 * st["edges_bitmap"] + 32.0 * st["bitmap_items"]
     cap = ncu_capture("k_tc_bitmap2") if world == 1 else None
     achieved = min_traffic / (bm_ms * 1e-3) / 1e9 if bm_ms > 0 else 0.0
     roofline = {

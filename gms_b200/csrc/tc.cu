@@ -39,14 +39,23 @@ namespace {
 //           k_classify      per vertex: hub or light, number of CTA items (cost-balanced), segment sizes
 //           two scans       item numbers and descriptor segments of the hubs
 //           k_plan_layout   per vertex: the counters become absolute write cursors (or a LIGHT / DEAD mark), items written
-//   pass 2  k_plan_scatter  one ATOM per edge takes the descriptor's slot in v's segment; edges into light vertices are
-//                           appended to the merge / gallop lists instead (warp-aggregated cursors)
+//   pass 2  k_plan_scatter  one ATOM per edge into an owned hub takes the descriptor's slot in v's segment; edges into
+//                           light vertices are appended to the merge / gallop lists instead (warp-aggregated cursors)
+// With part_count > 1 a device builds ITS SHARE of the schedule only: pass 1 and the classification are global (the
+// deal of the hubs needs every hub's work), everything after them — segments, items, cursors, descriptor writes, item
+// order — covers the hubs dealt to this device and the light edges whose slot number names it.
 // Round 1 emitted 251 M (key, descriptor) pairs at scale 24 and radix-sorted them (4 onesweep passes over 12 B per
 // pair + 2 x 251 M 64-bit atomics for the per-vertex work) and then flagged / scanned / compacted the light edges.
 constexpr int kCntShift = 38;                                  // counter word = (descriptors << 38) | sum of lengths
 constexpr unsigned long long kWorkMask = (1ull << kCntShift) - 1ull;
 constexpr unsigned long long kPosLight = 1ull << 63;           // cursor marks: edges into a light vertex ...
 constexpr unsigned long long kPosDead = 1ull << 62;            // ... and into a vertex that closes no triangle
+// What the scatter pass needs to know about the closing vertex v of an edge, one byte per vertex (the array stays in
+// the L2; the 24-byte cursor triples do not).  Only edges into a hub this device owns touch a cursor.
+constexpr uint8_t kDead = 0;        // no incoming descriptor can close a triangle
+constexpr uint8_t kLight = 1;       // edges go to the merge / gallop lists
+constexpr uint8_t kHub = 2;         // hub whose descriptor segment this device builds
+constexpr uint8_t kHubElsewhere = 3;        // hub dealt to another device (part_count > 1)
 
 __device__ __forceinline__ uint32_t len_class(eid_t len) { return len <= kShortLen ? 0u : (len <= kMidLen ? 1u : 2u); }
 
@@ -98,7 +107,8 @@ __global__ void k_classify(const eid_t *__restrict__ off, const vid_t *__restric
                            int64_t *__restrict__ nitems /* n+1 */, int64_t *__restrict__ seg /* n+1 */,
                            unsigned long long *__restrict__ cls /* [0]=hub edges [1]=hub wedges [2]=sum cnt*d+(v), hubs
                                                                   [3]=sum cnt*d+(v), all  [4]=light edges */,
-                           int *__restrict__ mx /* [0]=max span words [1]=max d+ of a hub */) {
+                           int *__restrict__ mx /* [0]=max span words [1]=max d+ of a hub */,
+                           uint8_t *__restrict__ vstate /* n: kDead / kLight / kHub */) {
     int mxw = 0, mxd = 0;
     unsigned long long he = 0, hw = 0, hb = 0, ab = 0, le = 0;
     for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v <= n; v += (int64_t)gridDim.x * blockDim.x) {
@@ -106,6 +116,7 @@ __global__ void k_classify(const eid_t *__restrict__ off, const vid_t *__restric
         if (v < n) {
             const unsigned long long w0 = cw[3 * v], w1 = cw[3 * v + 1], w2 = cw[3 * v + 2];
             const int64_t cnt = (int64_t)((w0 >> kCntShift) + (w1 >> kCntShift) + (w2 >> kCntShift));
+            uint8_t state = kDead;
             if (cnt > 0) {
                 const long long work = (long long)((w0 & kWorkMask) + (w1 & kWorkMask) + (w2 & kWorkMask));
                 const eid_t ob = off[v], oe = off[v + 1];
@@ -131,7 +142,9 @@ __global__ void k_classify(const eid_t *__restrict__ off, const vid_t *__restric
                     }
                 }
                 if (!hub) le += (unsigned long long)cnt;
+                state = hub ? kHub : kLight;
             }
+            vstate[v] = state;
         }
         nitems[v] = k;
         seg[v] = sg;
@@ -154,13 +167,17 @@ __global__ void k_classify(const eid_t *__restrict__ off, const vid_t *__restric
 // Counters -> write cursors; items of the hubs (a slice of the descriptor segment each, with its class boundaries).
 __global__ void k_plan_layout(int64_t n, unsigned long long *__restrict__ cw, const int64_t *__restrict__ nitems,
                               const int64_t *__restrict__ item_base, const int64_t *__restrict__ segbase,
-                              const int32_t *__restrict__ deal, Item *__restrict__ items) {
+                              const int32_t *__restrict__ deal, const uint8_t *__restrict__ vstate,
+                              Item *__restrict__ items) {
     for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x) {
         const int64_t c0 = (int64_t)(cw[3 * v] >> kCntShift), c1 = (int64_t)(cw[3 * v + 1] >> kCntShift),
                       c2 = (int64_t)(cw[3 * v + 2] >> kCntShift);
         const int64_t cnt = c0 + c1 + c2, k = nitems[v];
-        if (cnt == 0) { cw[3 * v] = kPosDead; cw[3 * v + 1] = kPosDead; cw[3 * v + 2] = kPosDead; continue; }
-        if (k == 0) { cw[3 * v] = kPosLight; cw[3 * v + 1] = kPosLight; cw[3 * v + 2] = kPosLight; continue; }
+        const uint8_t state = vstate[v];
+        if (state == kDead || state == kHubElsewhere) {
+            cw[3 * v] = kPosDead; cw[3 * v + 1] = kPosDead; cw[3 * v + 2] = kPosDead; continue;
+        }
+        if (state == kLight) { cw[3 * v] = kPosLight; cw[3 * v + 1] = kPosLight; cw[3 * v + 2] = kPosLight; continue; }
         const int64_t b = segbase[v];
         cw[3 * v] = (unsigned long long)b;
         cw[3 * v + 1] = (unsigned long long)(b + c0);
@@ -182,10 +199,11 @@ __global__ void k_plan_layout(int64_t n, unsigned long long *__restrict__ cw, co
 template <int G>
 __global__ void __launch_bounds__(256)
 k_plan_scatter(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, const int32_t *__restrict__ dplus,
-               int64_t n, unsigned long long *__restrict__ pos /* 3n */, uint64_t *__restrict__ desc, int variant,
-               int ratio, uint64_t *__restrict__ m_desc, vid_t *__restrict__ m_v, uint64_t *__restrict__ g_desc,
+               const uint8_t *__restrict__ vstate, int64_t n, unsigned long long *__restrict__ pos /* 3n */,
+               uint64_t *__restrict__ desc, int variant, int ratio, int part_index, int part_count,
+               uint64_t *__restrict__ m_desc, vid_t *__restrict__ m_v, uint64_t *__restrict__ g_desc,
                vid_t *__restrict__ g_v, unsigned long long *__restrict__ cursors /* [0]=merge [1]=gallop */,
-               unsigned long long *__restrict__ acc /* [0] = sum of d+(u) over hub edges */) {
+               unsigned long long *__restrict__ acc /* [0] = sum of d+(u) over hub edges (every device's) */) {
     namespace cg = cooperative_groups;
     const int sub = threadIdx.x % G;
     const int64_t grp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / G;
@@ -197,14 +215,16 @@ k_plan_scatter(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, con
             const eid_t len = e - s - 1;
             if (len <= 0) continue;
             const vid_t v = nbr[s];
-            const unsigned long long old = atomicAdd(&pos[3 * (int64_t)v + len_class(len)], 1ull);
-            if (old & kPosDead) continue;
+            const uint8_t state = vstate[v];
+            if (state == kDead) continue;
             const uint64_t ds = ((uint64_t)(s + 1) << kLenBits) | (uint64_t)len;
-            if (!(old & kPosLight)) {
-                desc[old] = ds;
+            if (state >= kHub) {
                 hub_u += (unsigned long long)(e - b);
+                if (state == kHub) desc[atomicAdd(&pos[3 * (int64_t)v + len_class(len)], 1ull)] = ds;
                 continue;
             }
+            // light edge: it belongs to the device its slot number names (the same rule the counting kernels apply)
+            if (part_count > 1 && (int)((uint64_t)(s + 1) % (uint64_t)part_count) != part_index) continue;
             const long long a = (long long)len, dv = dplus[v];
             const long long lo = a < dv ? a : dv, hi = a < dv ? dv : a;
             const bool gallop = variant == GMSB_TC_GALLOP || (variant != GMSB_TC_MERGE && hi >= (long long)ratio * lo);
@@ -268,6 +288,17 @@ __global__ void k_hub_keys(int64_t n, const int64_t *__restrict__ nitems, const 
 __global__ void k_hub_deal(const uint64_t *__restrict__ sorted, int nhubs, int32_t *__restrict__ deal) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nhubs; i += gridDim.x * blockDim.x)
         deal[sorted[i] & ((1ull << 26) - 1ull)] = i;
+}
+// part_count > 1: a device lays out, fills and orders only the segments of the hubs it owns; the others lose their
+// items and their segment before the scans, so nothing downstream sees them.
+__global__ void k_plan_own(int64_t n, const int32_t *__restrict__ deal, int part_index, int part_count,
+                           int64_t *__restrict__ nitems, int64_t *__restrict__ seg, uint8_t *__restrict__ vstate) {
+    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x) {
+        if (vstate[v] != kHub || snake_owner(deal[v], part_count) == part_index) continue;
+        vstate[v] = kHubElsewhere;
+        nitems[v] = 0;
+        seg[v] = 0;
+    }
 }
 
 // ---- counting kernels ----------------------------------------------------------------------------------------------
@@ -465,7 +496,7 @@ __device__ __forceinline__ uint32_t stream_class2(const uint64_t *__restrict__ d
 // VAR 0: the round-1 loops (stream_class); 1: stream_class2; 2: stream_class2 with the 128-bit body
 template <int BLOCK, int MINB, int VAR, bool NEAR>
 __global__ void __launch_bounds__(BLOCK, MINB)
-k_tc_bitmap2(const Item *__restrict__ items, int64_t first, int64_t stride, int64_t count, uint32_t cap_words,
+k_tc_bitmap2(const Item *__restrict__ items, int64_t count, uint32_t cap_words,
              const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, const uint64_t *__restrict__ desc,
              unsigned long long *__restrict__ total, unsigned int *__restrict__ ticket) {
     extern __shared__ uint32_t bm[];                  // cap_words + 1 words
@@ -481,8 +512,6 @@ k_tc_bitmap2(const Item *__restrict__ items, int64_t first, int64_t stride, int6
         const int64_t it = (int64_t)s_item;
         if (it >= count) break;
         const Item item = items[it];                                      // plan order: L2 tile, then heaviest
-        // several devices: whole hubs are dealt out (first = this device, stride = devices), see tc_plan.cuh
-        if (stride > 1 && snake_owner(item.deal, (int)stride) != (int)first) { __syncthreads(); continue; }
         const vid_t v = item.v;
         const eid_t ob = off[v], oe = off[v + 1];
         const uint32_t base = NEAR ? (((uint32_t)v + 1u) & ~31u) : (uint32_t)v + 1u;       // first element of the window
@@ -513,7 +542,7 @@ k_tc_bitmap2(const Item *__restrict__ items, int64_t first, int64_t stride, int6
 
 template <int BLOCK, int MINB, bool DEEP = false>
 __global__ void __launch_bounds__(BLOCK, MINB)
-k_tc_bitmap(const Item *__restrict__ items, int64_t first, int64_t stride, int64_t count, uint32_t cap_words,
+k_tc_bitmap(const Item *__restrict__ items, int64_t count, uint32_t cap_words,
             const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, const uint64_t *__restrict__ desc,
             unsigned long long *__restrict__ total, unsigned int *__restrict__ ticket) {
     extern __shared__ uint32_t bm[];                  // cap_words + 1 words
@@ -529,8 +558,6 @@ k_tc_bitmap(const Item *__restrict__ items, int64_t first, int64_t stride, int64
         const int64_t it = (int64_t)s_item;
         if (it >= count) break;
         const Item item = items[it];                                      // plan order: L2 tile, then heaviest
-        // several devices: whole hubs are dealt out (first = this device, stride = devices), see tc_plan.cuh
-        if (stride > 1 && snake_owner(item.deal, (int)stride) != (int)first) { __syncthreads(); continue; }
         const vid_t v = item.v;
         const eid_t ob = off[v], oe = off[v + 1];
         const uint32_t base = (uint32_t)v + 1u;
@@ -553,7 +580,7 @@ k_tc_bitmap(const Item *__restrict__ items, int64_t first, int64_t stride, int64
 
 // Galloping kernel: one warp per light edge (isect.cuh: warp_gallop_count).
 __global__ void __launch_bounds__(256)
-k_tc_gallop(const uint64_t *__restrict__ desc, const vid_t *__restrict__ vs, int64_t first, int64_t stride,
+k_tc_gallop(const uint64_t *__restrict__ desc, const vid_t *__restrict__ vs,
             int64_t count, const eid_t *__restrict__ off, const vid_t *__restrict__ nbr,
             unsigned long long *__restrict__ total) {
     __shared__ unsigned long long red[8];
@@ -563,9 +590,6 @@ k_tc_gallop(const uint64_t *__restrict__ desc, const vid_t *__restrict__ vs, int
     uint32_t hits = 0;
     for (int64_t i = warp; i < count; i += nwarps) {
         const uint64_t ds = desc[i];
-        // several devices: a light edge belongs to the device its slot number names (the order of the list itself
-        // depends on the atomics of the scatter pass)
-        if (stride > 1 && (int64_t)((ds >> kLenBits) % (uint64_t)stride) != first) continue;
         const vid_t v = vs[i];
         const eid_t ob = off[v];
         hits += warp_gallop_count(nbr + (ds >> kLenBits), (int)(ds & kLenMask), nbr + ob, (int)(off[v + 1] - ob), lane);
@@ -583,7 +607,7 @@ constexpr int kMergeWarps = 8;
 
 template <bool BLOCK>
 __global__ void __launch_bounds__(kMergeWarps * 32)
-k_tc_merge(const uint64_t *__restrict__ desc, const vid_t *__restrict__ vs, int64_t first, int64_t stride,
+k_tc_merge(const uint64_t *__restrict__ desc, const vid_t *__restrict__ vs,
            int64_t count, const eid_t *__restrict__ off, const vid_t *__restrict__ nbr,
            unsigned long long *__restrict__ total) {
     __shared__ vid_t stage[BLOCK ? 1 : kMergeWarps][BLOCK ? 1 : kMergeTile + 2];
@@ -594,7 +618,6 @@ k_tc_merge(const uint64_t *__restrict__ desc, const vid_t *__restrict__ vs, int6
     uint32_t hits = 0;
     for (int64_t i = warp; i < count; i += nwarps) {
         const uint64_t ds = desc[i];
-        if (stride > 1 && (int64_t)((ds >> kLenBits) % (uint64_t)stride) != first) continue;
         const vid_t v = vs[i];
         const eid_t ob = off[v];
         if constexpr (BLOCK)
@@ -620,7 +643,8 @@ gmsb_tc_options normalise(const gmsb_tc_options *in) {
 
 bool same_plan(const gmsb_tc_options &a, const gmsb_tc_options &b) {
     return a.variant == b.variant && a.hub_bitmap_bits == b.hub_bitmap_bits && a.gallop_ratio == b.gallop_ratio &&
-           a.hub_min_work == b.hub_min_work && a.reserved[0] == b.reserved[0] && a.reserved[1] == b.reserved[1];
+           a.hub_min_work == b.hub_min_work && a.reserved[0] == b.reserved[0] && a.reserved[1] == b.reserved[1] &&
+           a.part_index == b.part_index && a.part_count == b.part_count;      // a schedule holds one device's share
     // (reserved[2], reserved[3] pick kernel builds, not the schedule)
 }
 
@@ -630,6 +654,7 @@ TcPlan *build_plan(const Dag &d, const gmsb_tc_options &opt) {
     try {
         p->opt = opt;
         const int64_t n = d.n, m = d.m;
+        const int P = opt.part_count, pi = opt.part_index;
         GMSB_REQUIRE(d.max_dplus < (1 << kLenBits), "tc: out-degree too large for the descriptor format");
         GMSB_REQUIRE(m < (int64_t(1) << (64 - kLenBits)), "tc: too many edges for the descriptor format");
         // the per-(vertex, class) counter packs (descriptors << 38 | sum of suffix lengths)
@@ -650,13 +675,12 @@ TcPlan *build_plan(const Dag &d, const gmsb_tc_options &opt) {
         launched();
         tr.mark("plan: count pass");
         DevBuf<int64_t> nitems(n + 1), seg(n + 1), item_base(n + 1), segbase(n + 1);
+        DevBuf<uint8_t> vstate(n);
         PlanParams pp{opt.variant, hub_bits, (long long)opt.hub_min_work,
                       opt.reserved[0] > 0 ? (long long)opt.reserved[0] : 262144ll};
         k_classify<<<grid_for(n + 1, 256), 256, 0, r.stream>>>(d.off.p, d.nbr.p, n, cw.p, pp, nitems.p, seg.p, cls.p,
-                                                              mx.p);
+                                                              mx.p, vstate.p);
         launched();
-        exclusive_sum(nitems.p, item_base.p, n + 1);
-        exclusive_sum(seg.p, segbase.p, n + 1);
         unsigned long long h_acc[4], h_cls[5];
         int h_mx[2];
         acc.download(h_acc, 4);
@@ -666,16 +690,13 @@ TcPlan *build_plan(const Dag &d, const gmsb_tc_options &opt) {
         p->wedges = h_acc[1];
         p->n_desc = (int64_t)h_acc[2];
         p->bytes_kept = 4ull * (h_acc[3] + h_cls[3]);
-        p->n_bitmap_edges = (int64_t)h_cls[0];
         p->wedges_bitmap = h_cls[1];
         p->max_span_words = h_mx[0];
         p->max_hub_dplus = h_mx[1];
         const int64_t n_light = (int64_t)h_cls[4];
-        tr.mark("plan: classify + scans");
         if (p->n_desc == 0) return p;
-        p->n_items = item_base.get(n);
-        p->items.alloc(p->n_items);
-        p->desc.alloc(p->n_bitmap_edges);
+        // whole hubs are dealt to the devices (deal = position by descending work); with several devices the ones
+        // dealt elsewhere drop out here, before the scans lay out items and segments
         GMSB_REQUIRE(n <= (int64_t(1) << 26), "tc: too many vertices for the hub deal key");
         DevBuf<int32_t> deal(n);
         {
@@ -687,12 +708,24 @@ TcPlan *build_plan(const Dag &d, const gmsb_tc_options &opt) {
             if (n_hubs) {
                 uint64_t *sorted = radix_sort_keys(hk.p, hk2.p, n_hubs, 0, 64);
                 k_hub_deal<<<grid_for(n_hubs, 256), 256, 0, r.stream>>>(sorted, n_hubs, deal.p); launched();
+                if (P > 1) {
+                    k_plan_own<<<grid_for(n, 256), 256, 0, r.stream>>>(n, deal.p, pi, P, nitems.p, seg.p, vstate.p);
+                    launched();
+                }
             }
         }
-        k_plan_layout<<<grid_for(n, 256), 256, 0, r.stream>>>(n, cw.p, nitems.p, item_base.p, segbase.p, deal.p,
+        exclusive_sum(nitems.p, item_base.p, n + 1);
+        exclusive_sum(seg.p, segbase.p, n + 1);
+        tr.mark("plan: classify + scans");
+        p->n_items = item_base.get(n);
+        p->n_bitmap_edges = segbase.get(n);
+        p->items.alloc(p->n_items);
+        p->desc.alloc(p->n_bitmap_edges);
+        k_plan_layout<<<grid_for(n, 256), 256, 0, r.stream>>>(n, cw.p, nitems.p, item_base.p, segbase.p, deal.p, vstate.p,
                                                              p->items.p);
         launched();
-        // both light lists are sized for all light edges; the scatter pass decides merge / gallop per edge
+        // both light lists are sized for all light edges (an upper bound for this device's share: light edges are dealt
+        // by slot number); the scatter pass decides merge / gallop per edge
         p->m_desc.alloc(n_light); p->m_v.alloc(n_light); p->g_desc.alloc(n_light); p->g_v.alloc(n_light);
         DevBuf<unsigned long long> cursors(2), hub_u(1);
         cursors.zero(); hub_u.zero();
@@ -701,8 +734,8 @@ TcPlan *build_plan(const Dag &d, const gmsb_tc_options &opt) {
         // against 9.4 ms; the two passes over the tile and the 48 KB of shared cursors per CTA cost more than the
         // returns of the global atomics.)
         k_plan_scatter<G><<<grid_for(n * G, 256), 256, 0, r.stream>>>(
-            d.off.p, d.nbr.p, d.dplus.p, n, cw.p, p->desc.p, opt.variant, opt.gallop_ratio, p->m_desc.p, p->m_v.p,
-            p->g_desc.p, p->g_v.p, cursors.p, hub_u.p);
+            d.off.p, d.nbr.p, d.dplus.p, vstate.p, n, cw.p, p->desc.p, opt.variant, opt.gallop_ratio, pi, P, p->m_desc.p,
+            p->m_v.p, p->g_desc.p, p->g_v.p, cursors.p, hub_u.p);
         launched();
         unsigned long long h_cur[2];
         cursors.download(h_cur, 2);
@@ -743,8 +776,6 @@ TcPlan *build_plan(const Dag &d, const gmsb_tc_options &opt) {
     return p;
 }
 
-int64_t part_size(int64_t total, int idx, int parts) { return total > idx ? (total - idx + parts - 1) / parts : 0; }
-
 }  // namespace
 
 gmsb_tc_options normalise_tc_options(const gmsb_tc_options *in) { return normalise(in); }
@@ -778,8 +809,8 @@ void tc_total(Graph &g, const gmsb_tc_options &opt_in, uint64_t *out, gmsb_tc_st
     DevBuf<unsigned long long> total(1);
     total.zero();
     const int P = opt.part_count, pi = opt.part_index;
-    // every device walks the whole item / light lists and keeps what it owns (whole hubs by deal position, light edges
-    // by slot number): ownership must not depend on the order the scatter pass's atomics ran in
+    // the schedule holds this device's share only (whole hubs by deal position, light edges by slot number: ownership
+    // does not depend on the order the scatter pass's atomics ran in)
     const int64_t my_items = p.n_items, my_merge = p.n_merge, my_gallop = p.n_gallop;
 
     t_bm.start();
@@ -798,7 +829,7 @@ void tc_total(Graph &g, const gmsb_tc_options &opt_in, uint64_t *out, gmsb_tc_st
             GMSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, BLOCK, smem));
             GMSB_REQUIRE(resident >= 1, "tc: bitmap kernel does not fit on an SM");
             const int grid = (int)std::min<int64_t>(mine, (int64_t)r.sm_count * resident);
-            kern<<<grid, BLOCK, smem, r.stream>>>(items, pi, P, mine, (uint32_t)cap_words, d.off.p, d.nbr.p,
+            kern<<<grid, BLOCK, smem, r.stream>>>(items, mine, (uint32_t)cap_words, d.off.p, d.nbr.p,
                                                   p.desc.p, total.p, ticket);
             launched();
         };
@@ -831,10 +862,10 @@ void tc_total(Graph &g, const gmsb_tc_options &opt_in, uint64_t *out, gmsb_tc_st
     if (my_merge) {
         int grid = (int)std::min<int64_t>(ceil_div(my_merge, kMergeWarps), (int64_t)r.sm_count * 16);
         if (opt.reserved[3] == 1)
-            k_tc_merge<true><<<grid, kMergeWarps * 32, 0, r.stream>>>(p.m_desc.p, p.m_v.p, pi, P, my_merge, d.off.p,
+            k_tc_merge<true><<<grid, kMergeWarps * 32, 0, r.stream>>>(p.m_desc.p, p.m_v.p, my_merge, d.off.p,
                                                                       d.nbr.p, total.p);
         else
-            k_tc_merge<false><<<grid, kMergeWarps * 32, 0, r.stream>>>(p.m_desc.p, p.m_v.p, pi, P, my_merge, d.off.p,
+            k_tc_merge<false><<<grid, kMergeWarps * 32, 0, r.stream>>>(p.m_desc.p, p.m_v.p, my_merge, d.off.p,
                                                                        d.nbr.p, total.p);
         launched();
     }
@@ -842,7 +873,7 @@ void tc_total(Graph &g, const gmsb_tc_options &opt_in, uint64_t *out, gmsb_tc_st
     t_gl.start();
     if (my_gallop) {
         int grid = (int)std::min<int64_t>(ceil_div(my_gallop, 8), (int64_t)r.sm_count * 16);
-        k_tc_gallop<<<grid, 256, 0, r.stream>>>(p.g_desc.p, p.g_v.p, pi, P, my_gallop, d.off.p, d.nbr.p, total.p);
+        k_tc_gallop<<<grid, 256, 0, r.stream>>>(p.g_desc.p, p.g_v.p, my_gallop, d.off.p, d.nbr.p, total.p);
         launched();
     }
     t_gl.stop();
@@ -854,9 +885,9 @@ void tc_total(Graph &g, const gmsb_tc_options &opt_in, uint64_t *out, gmsb_tc_st
         s.algorithmic_bytes = p.algorithmic_bytes / P + (pi == 0 ? p.algorithmic_bytes % P : 0);
         s.wedges_checked = p.wedges / P;
         s.oriented_edges = d.m;
-        s.edges_bitmap = part_size(p.n_bitmap_edges, pi, P);
-        s.edges_merge = part_size(p.n_merge, pi, P);          // (shares by count; ownership is by hub / by slot number)
-        s.edges_gallop = part_size(p.n_gallop, pi, P);
+        s.edges_bitmap = p.n_bitmap_edges;                    // this device's share, like bitmap_items
+        s.edges_merge = p.n_merge;
+        s.edges_gallop = p.n_gallop;
         s.ms_orient = t_orient.ms();
         s.ms_bitmap = t_bm.ms();
         s.ms_merge = t_mg.ms();

@@ -65,7 +65,7 @@ __device__ __forceinline__ void support_class(const uint64_t *__restrict__ dptr,
 
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
-k_support_bitmap(const Item *__restrict__ items, int64_t first, int64_t stride, int64_t count, uint32_t cap_words,
+k_support_bitmap(const Item *__restrict__ items, int64_t count, uint32_t cap_words,
                  int max_dplus,
                  const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, const uint64_t *__restrict__ desc,
                  uint32_t *__restrict__ sup, unsigned int *__restrict__ ticket) {
@@ -84,7 +84,6 @@ k_support_bitmap(const Item *__restrict__ items, int64_t first, int64_t stride, 
         const int64_t it = (int64_t)s_item;
         if (it >= count) break;
         const Item item = items[it];
-        if (stride > 1 && snake_owner(item.deal, (int)stride) != (int)first) { __syncthreads(); continue; }
         const vid_t v = item.v;
         const eid_t ob = off[v];
         const int dv = (int)(off[v + 1] - ob);
@@ -111,14 +110,13 @@ k_support_bitmap(const Item *__restrict__ items, int64_t first, int64_t stride, 
 
 // Light edges: one warp per edge, lanes binary-search elements of the shorter list in the longer one.
 __global__ void __launch_bounds__(256)
-k_support_light(const uint64_t *__restrict__ desc, const vid_t *__restrict__ vs, int64_t first, int64_t stride,
+k_support_light(const uint64_t *__restrict__ desc, const vid_t *__restrict__ vs,
                 int64_t count, const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, uint32_t *__restrict__ sup) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t i = warp; i < count; i += nwarps) {
         const uint64_t ds = desc[i];
-        if (stride > 1 && (int64_t)((ds >> kLenBits) % (uint64_t)stride) != first) continue;
         const vid_t v = vs[i];
         const int64_t sa = (int64_t)(ds >> kLenBits), sb = off[v];
         const int na = (int)(ds & kLenMask), nb = (int)(off[v + 1] - sb);
@@ -209,13 +207,15 @@ __global__ void k_edge_scores(const eid_t *__restrict__ off, const vid_t *__rest
 void tc_support(Graph &g, DevBuf<uint32_t> &sup, int pi, int P) {
     Runtime &r = rt();
     gmsb_tc_options opt = normalise_tc_options(nullptr);
+    GMSB_REQUIRE(P >= 1 && pi >= 0 && pi < P, "tc_support: bad partition");
     opt.reuse_plan = 1;
+    opt.part_index = pi; opt.part_count = P;          // the schedule is built for this device's share
     TcPlan &p = ensure_plan(g, opt);
     Dag &d = *g.dag;
     sup.alloc(d.m);
     sup.zero();
     if (d.m == 0) return;
-    const int64_t my_items = p.n_items;         // every device walks all items and keeps the hubs it owns
+    const int64_t my_items = p.n_items;
     if (my_items) {
         constexpr int BLOCK = 512;
         auto kern = k_support_bitmap<BLOCK>;
@@ -229,7 +229,7 @@ void tc_support(Graph &g, DevBuf<uint32_t> &sup, int pi, int P) {
         const int grid = (int)std::min<int64_t>(my_items, (int64_t)r.sm_count * resident);
         DevBuf<unsigned int> ticket(1);
         ticket.zero();
-        kern<<<grid, BLOCK, smem, r.stream>>>(p.items.p, pi, P, my_items, (uint32_t)p.max_span_words, p.max_hub_dplus,
+        kern<<<grid, BLOCK, smem, r.stream>>>(p.items.p, my_items, (uint32_t)p.max_span_words, p.max_hub_dplus,
                                               d.off.p, d.nbr.p, p.desc.p, sup.p, ticket.p);
         launched();
         GMSB_CUDA(cudaStreamSynchronize(r.stream));
@@ -237,12 +237,12 @@ void tc_support(Graph &g, DevBuf<uint32_t> &sup, int pi, int P) {
     const int64_t my_merge = p.n_merge, my_gallop = p.n_gallop;
     if (my_merge) {
         int grid = (int)std::min<int64_t>(ceil_div(my_merge, 8), (int64_t)r.sm_count * 16);
-        k_support_light<<<grid, 256, 0, r.stream>>>(p.m_desc.p, p.m_v.p, pi, P, my_merge, d.off.p, d.nbr.p, sup.p);
+        k_support_light<<<grid, 256, 0, r.stream>>>(p.m_desc.p, p.m_v.p, my_merge, d.off.p, d.nbr.p, sup.p);
         launched();
     }
     if (my_gallop) {
         int grid = (int)std::min<int64_t>(ceil_div(my_gallop, 8), (int64_t)r.sm_count * 16);
-        k_support_light<<<grid, 256, 0, r.stream>>>(p.g_desc.p, p.g_v.p, pi, P, my_gallop, d.off.p, d.nbr.p, sup.p);
+        k_support_light<<<grid, 256, 0, r.stream>>>(p.g_desc.p, p.g_v.p, my_gallop, d.off.p, d.nbr.p, sup.p);
         launched();
     }
 }

@@ -126,13 +126,18 @@ def test_partition_sums_to_total(kron12, golden):
     want = golden["generated"]["kronecker-12"]["tc"]
     for parts in (2, 3, 8):
         for v in ("auto", "merge", "bitmap"):
-            tot, bytes_ = 0, 0
+            tot, bytes_, edges = 0, 0, [0, 0, 0, 0]
             for p in range(parts):
                 c, st = g.tc_total_ex(variant=v, part_index=p, part_count=parts, reuse_plan=True)
                 tot += c
                 bytes_ += st["algorithmic_bytes"]
+                for i, key in enumerate(("edges_bitmap", "edges_merge", "edges_gallop", "bitmap_items")):
+                    edges[i] += st[key]
             assert tot == want, (parts, v)
-            assert bytes_ == g.tc_total_ex(reuse_plan=True)[1]["algorithmic_bytes"]
+            _, full = g.tc_total_ex(variant=v, reuse_plan=True)
+            assert bytes_ == full["algorithmic_bytes"]
+            # a device builds only its share of the schedule: the shares cover every edge / hub item exactly once
+            assert edges == [full[key] for key in ("edges_bitmap", "edges_merge", "edges_gallop", "bitmap_items")]
 
 
 def test_algorithmic_bytes_match_definition(kron12, orc):
