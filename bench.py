@@ -269,18 +269,18 @@ def kclique_cpu_baseline(args, G, scale=16):
 
 
 def run_e2e(args, G, gd, off_h, nbr_h, n, slots, m, opts, expect, world, dev):
-    """host CSR -> HBM -> orient -> schedule -> count -> result, nothing cached.  N > 1: rank r uploads slice r/N of the
-    pinned CSR and the slices are all-gathered over NVLink (gms_b200/dist.py), so the host copy is read once instead of N
-    times; N = 1: the C-ABI call on the host buffers (gmsb_graph_from_csr_ex, upload pipelined with the orientation)."""
+    """host CSR -> HBM -> orient -> schedule -> count -> result, nothing cached.  N = 1: the C-ABI call on the host
+    buffers (gmsb_graph_from_csr_ex, upload pipelined with the orientation).  N > 1: the sharded build (gmsb_shard_*,
+    gms_b200/dist.py: ShardedOrientedBuild) — rank r uploads and orients vertex range r of N, the finished rows are
+    all-gathered over NVLink, so the host copy is read once and the orientation passes are split N ways."""
     import torch
-    sharded = gd.ShardedCsrUpload(off_h, nbr_h[:slots], dev) if world > 1 else None
+    sharded = gd.ShardedOrientedBuild(off_h, nbr_h[:slots], dev) if world > 1 else None
 
     def e2e_step():
         if sharded is None:
             gg = G.Graph.from_csr(off_h.numpy(), nbr_h.numpy()[:slots], orient=True)   # GMSB_BUILD_ORIENT
         else:
-            off_d, nbr_d = sharded.upload()
-            gg = G.Graph.from_csr_device(n, off_d.data_ptr(), nbr_d.data_ptr())
+            gg = sharded.build()
         c, s2 = gg.tc_total_ex(reuse_plan=False, **opts)
         gg.free()
         return c, s2
@@ -394,9 +394,9 @@ def run_ours(args):
     value = m * args.steps / (ms_total * 1e-3)
 
     # ---- e2e: host CSR -> HBM -> orient -> schedule -> count -> result, nothing cached
-    # N > 1: rank r uploads slice r/N of the pinned CSR and the slices are all-gathered over NVLink (gms_b200/dist.py),
-    # so the host copy is read once instead of N times; N = 1: the plain C-ABI call on the host buffers.
-    e2e_value, e2e_ms, e2e_steps, e2e_orient, h2d = None, float("nan"), 1, [float("nan")], 8 * (n + 1) + 4 * slots
+    # N = 1: the plain C-ABI call on the host buffers; N > 1: the sharded build (every rank uploads the offsets and its own
+    # vertex range of the neighbour array; h2d counts all ranks)
+    e2e_value, e2e_ms, e2e_steps, e2e_orient, h2d = None, float("nan"), 1, [float("nan")], world * 8 * (n + 1) + 4 * slots
     if not args.no_e2e:
         e2e_value, e2e_ms, e2e_steps, e2e_orient = run_e2e(args, G, gd, off_h, nbr_h, n, slots, m, opts, expect, world, dev)
 
@@ -449,8 +449,11 @@ def run_ours(args):
         "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
                 "ms_per_step": e2e_ms / e2e_steps, "schedule_and_rest_ms": float(np.mean(e2e_orient)),
-                "note": "gmsb_graph_from_csr_ex(GMSB_BUILD_ORIENT) from pinned host memory (upload pipelined with the "
-                        "ranking / validation / relabel passes) + gmsb_tc_total_ex with nothing cached + result"},
+                "note": ("gmsb_graph_from_csr_ex(GMSB_BUILD_ORIENT) from pinned host memory (upload pipelined with the "
+                         "ranking / validation / orientation passes) + gmsb_tc_total_ex with nothing cached + result"
+                         if world == 1 else
+                         "gmsb_shard_begin / export / finish from pinned host memory (each rank uploads and orients one "
+                         "vertex range; pieces all-gathered over NVLink) + gmsb_tc_total_ex with nothing cached + result")},
     }
 
     if args.no_e2e:

@@ -66,6 +66,11 @@ SIGNATURES = {
     "gmsb_graph_from_csr": (C.c_int, [C.c_int64, _i64p, _i32p, C.c_int, C.POINTER(C.c_void_p)]),
     "gmsb_graph_from_csr_ex": (C.c_int, [C.c_int64, _i64p, _i32p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "gmsb_graph_from_csr_device": (C.c_int, [C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "gmsb_shard_begin": (C.c_int, [C.c_int64, _i64p, _i32p, C.c_int, C.c_int, C.POINTER(C.c_void_p),
+                                   C.POINTER(C.c_int64)]),
+    "gmsb_shard_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gmsb_shard_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "gmsb_shard_free": (C.c_int, [C.c_void_p]),
     "gmsb_graph_from_edgelist": (C.c_int, [C.c_int64, _i32p, _i32p, C.c_int, C.POINTER(C.c_void_p)]),
     "gmsb_graph_from_edgelist_device": (C.c_int, [C.c_int64, C.c_void_p, C.c_void_p, C.c_int,
                                                   C.POINTER(C.c_void_p)]),
@@ -401,6 +406,41 @@ class Graph:
 
 
 SET_OPS = {"intersect": 0, "union": 1, "difference": 2}
+
+
+class Shard:
+    """One device's share of a sharded build of the oriented representation (gmsb_shard_*): `begin` uploads and orients
+    the vertex range of part `part_index`; the caller exchanges the exported pieces; `finish` returns a Graph that
+    answers the triangle entry points."""
+
+    def __init__(self, offsets, nbrs, part_index, part_count):
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        h, plen = C.c_void_p(), C.c_int64()
+        _check(lib().gmsb_shard_begin(len(offsets) - 1, offsets, _ids(nbrs), int(part_index), int(part_count),
+                                      C.byref(h), C.byref(plen)))
+        self.h, self.piece_len = h, plen.value
+
+    def export(self, piece_ptr, dplus_all_ptr):
+        """piece_ptr: device int32[>= piece_len]; dplus_all_ptr: device int32[n], zeroed by the caller."""
+        _check(lib().gmsb_shard_export(self.h, C.c_void_p(piece_ptr), C.c_void_p(dplus_all_ptr)))
+
+    def finish(self, pieces_ptr, piece_stride, dplus_all_ptr):
+        g = C.c_void_p()
+        _check(lib().gmsb_shard_finish(self.h, C.c_void_p(pieces_ptr), int(piece_stride), C.c_void_p(dplus_all_ptr),
+                                       C.byref(g)))
+        self.free()
+        return Graph(g)
+
+    def free(self):
+        if self.h:
+            lib().gmsb_shard_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 class DeviceSet:

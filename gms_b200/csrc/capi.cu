@@ -141,9 +141,17 @@ int guarded(F &&f) {
     }
 }
 
-inline Graph &G(gmsb_graph_t h) {
+// any handle: entry points that work on the oriented representation alone (or on the handle's metadata)
+inline Graph &Gdag(gmsb_graph_t h) {
     GMSB_REQUIRE(h != nullptr, "null graph handle");
     return *reinterpret_cast<Graph *>(h);
+}
+// handles with complete symmetric lists: everything else
+inline Graph &G(gmsb_graph_t h) {
+    Graph &g = Gdag(h);
+    GMSB_REQUIRE(!g.dag_only, "this handle comes from a sharded build and holds the oriented representation only "
+                              "(triangle counts); build it with gmsb_graph_from_csr for the other operators");
+    return g;
 }
 
 }  // namespace gmsb
@@ -253,6 +261,29 @@ GMSB_API int gmsb_graph_from_csr_device(int64_t n, const int64_t *off, const int
         *out = reinterpret_cast<gmsb_graph_t>(graph_from_csr_device(n, off, nbr, directed != 0, false));
     });
 }
+// sharded construction of the oriented representation (graph_build.cu: shard_*)
+GMSB_API int gmsb_shard_begin(int64_t n, const int64_t *off, const int32_t *nbr, int part_index, int part_count,
+                              gmsb_shard_t *out, int64_t *piece_len) {
+    return guarded([&] {
+        GMSB_REQUIRE(out, "null output handle");
+        *out = reinterpret_cast<gmsb_shard_t>(shard_begin(n, off, nbr, part_index, part_count, piece_len));
+    });
+}
+GMSB_API int gmsb_shard_export(gmsb_shard_t s, int32_t *piece_dev, int32_t *dplus_all_dev) {
+    return guarded([&] {
+        GMSB_REQUIRE(s, "null shard handle");
+        shard_export(*reinterpret_cast<Shard *>(s), piece_dev, dplus_all_dev);
+    });
+}
+GMSB_API int gmsb_shard_finish(gmsb_shard_t s, const int32_t *pieces_dev, int64_t piece_stride, const int32_t *dplus_all_dev,
+                               gmsb_graph_t *out) {
+    return guarded([&] {
+        GMSB_REQUIRE(s && out, "null handle");
+        *out = reinterpret_cast<gmsb_graph_t>(shard_finish(*reinterpret_cast<Shard *>(s), pieces_dev, piece_stride,
+                                                           dplus_all_dev));
+    });
+}
+GMSB_API int gmsb_shard_free(gmsb_shard_t s) { return guarded([&] { delete reinterpret_cast<Shard *>(s); }); }
 GMSB_API int gmsb_graph_from_edgelist(int64_t m, const int32_t *src, const int32_t *dst, int symmetrize, gmsb_graph_t *out) {
     return guarded([&] {
         GMSB_REQUIRE(out, "null output handle");
@@ -277,13 +308,13 @@ GMSB_API int gmsb_graph_relabel_by_degree(gmsb_graph_t g, gmsb_graph_t *out) {
     });
 }
 GMSB_API int gmsb_graph_num_nodes(gmsb_graph_t g, int64_t *n) {
-    return guarded([&] { GMSB_REQUIRE(n, "null argument"); *n = G(g).n; });
+    return guarded([&] { GMSB_REQUIRE(n, "null argument"); *n = Gdag(g).n; });
 }
 GMSB_API int gmsb_graph_num_slots(gmsb_graph_t g, int64_t *s) {
-    return guarded([&] { GMSB_REQUIRE(s, "null argument"); *s = G(g).slots; });
+    return guarded([&] { GMSB_REQUIRE(s, "null argument"); *s = Gdag(g).slots; });
 }
 GMSB_API int gmsb_graph_is_directed(gmsb_graph_t g, int *d) {
-    return guarded([&] { GMSB_REQUIRE(d, "null argument"); *d = G(g).directed ? 1 : 0; });
+    return guarded([&] { GMSB_REQUIRE(d, "null argument"); *d = Gdag(g).directed ? 1 : 0; });
 }
 GMSB_API int gmsb_graph_export_csr(gmsb_graph_t g, int64_t *off, int32_t *nbr) {
     return guarded([&] {
@@ -367,7 +398,7 @@ GMSB_API int gmsb_tc_total_ex(gmsb_graph_t g, const gmsb_tc_options *opt, uint64
     return guarded([&] {
         gmsb_tc_options o{};
         if (opt) o = *opt;
-        tc_total(G(g), o, out, stats);
+        tc_total(Gdag(g), o, out, stats);
     });
 }
 GMSB_API int gmsb_tc_total(gmsb_graph_t g, uint64_t *out) {
@@ -377,7 +408,7 @@ GMSB_API int gmsb_tc_total(gmsb_graph_t g, uint64_t *out) {
 }
 GMSB_API int gmsb_tc_vertex2(gmsb_graph_t g, int64_t *out_n) {
     return guarded([&] {
-        Graph &gr = G(g);
+        Graph &gr = Gdag(g);
         GMSB_REQUIRE(out_n || gr.n == 0, "null output");
         tc_vertex2(gr, out_n);
     });

@@ -154,6 +154,7 @@ struct Graph {
     DevBuf<vid_t> nbr;          // slots, ascending within each list
     Dag *dag = nullptr;         // cached degree-oriented DAG (undirected graphs only)
     bool dag_pinned = false;    // the DAG was built with the graph (GMSB_BUILD_ORIENT): reuse_plan = 0 keeps it
+    bool dag_only = false;      // sharded build: only the oriented representation is complete on this device (nbr is not)
     void *replicas = nullptr;   // copies on the other devices of gmsb_set_devices (mgpu.cu)
     void (*release_replicas)(void *) = nullptr;
     ~Graph();

@@ -192,10 +192,86 @@ Graph *graph_from_csr_device(int64_t n, const eid_t *off, const vid_t *nbr, bool
 }
 
 // gmsb_graph_from_csr_ex(GMSB_BUILD_ORIENT): the host CSR is uploaded in chunks on a copy stream while the library
-// stream already works on what has arrived — the degree ranking needs the offsets only (the first 6 % of the bytes),
-// the validation and the relabel + count pass of the orientation run per vertex range as soon as that range's
-// neighbour slots are on the device.  When the last chunk lands only the emit + sort passes are left.  (Host memory
-// should be pinned; with pageable memory the copies are staged by the driver and overlap less.)
+// stream already works on what has arrived — the degree ranking needs the offsets only (the first 6 % of the bytes);
+// the validation and the relabel / emit / sort passes of the orientation run per vertex range as soon as that range's
+// neighbour slots are on the device.  When the last chunk lands only that chunk's passes and the move of the finished
+// rows into rank order are left.  (Host memory should be pinned; with pageable memory the copies are staged by the
+// driver and overlap less.)
+namespace {
+struct UploadStreams {
+    cudaStream_t copy = nullptr;
+    std::vector<cudaEvent_t> ev;
+    ~UploadStreams() {
+        for (auto e : ev) cudaEventDestroy(e);
+        if (copy) cudaStreamDestroy(copy);
+    }
+    cudaEvent_t mark() {
+        cudaEvent_t e;
+        GMSB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ev.push_back(e);
+        GMSB_CUDA(cudaEventRecord(e, copy));
+        return e;
+    }
+};
+
+// Uploads the offsets and the neighbour slots of the vertex range [u0, u1) (the whole graph, or one device's share of
+// it) in `chunks` pieces of about equal slot counts and runs the orientation passes on every piece as it lands.
+// flags[0] is raised by an id outside [0, n); desc[1] counts the descents between consecutive slots.
+void upload_and_orient_range(Graph *g, OrientPipeline &pipe, UploadStreams &st, const eid_t *off, const vid_t *nbr,
+                             int64_t u0, int64_t u1, int chunks, DevBuf<int> &flags, DevBuf<unsigned long long> &desc) {
+    Runtime &r = rt();
+    const int64_t n = g->n;
+    const eid_t last = g->slots;
+    GMSB_CUDA(cudaStreamCreateWithFlags(&st.copy, cudaStreamNonBlocking));
+    // allocations above may have been served from blocks whose last use is still queued on the library stream
+    GMSB_CUDA(cudaStreamSynchronize(r.stream));
+    GMSB_CUDA(cudaMemcpyAsync(g->off.p, off, sizeof(eid_t) * (n + 1), cudaMemcpyHostToDevice, st.copy));
+    cudaEvent_t ev_off = st.mark();
+    // vertex ranges of about equal slot counts (the host array is only used to pick the cuts: a malformed one is
+    // caught by the device check of the offsets below before any range is processed)
+    auto clamp = [&](eid_t x) { return x < 0 ? eid_t(0) : (x > last ? last : x); };
+    const eid_t lo_slot = clamp(off[u0]), hi_slot = std::max(lo_slot, clamp(off[u1]));
+    std::vector<int64_t> cut(1, u0);
+    for (int c = 1; c < chunks; ++c) {
+        const eid_t target = lo_slot + (hi_slot - lo_slot) / chunks * c;
+        int64_t lo = cut.back(), hi = u1;
+        while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (off[mid] < target) lo = mid + 1; else hi = mid; }
+        cut.push_back(lo);
+    }
+    cut.push_back(u1);
+    std::vector<cudaEvent_t> ev_chunk;
+    std::vector<eid_t> upto_slot;
+    eid_t sent = lo_slot;
+    for (int c = 0; c < chunks; ++c) {
+        eid_t upto = c + 1 == chunks ? hi_slot : off[cut[c + 1]];
+        if (upto < sent || upto > hi_slot) upto = sent;                     // malformed offsets: rejected below
+        if (upto > sent)
+            GMSB_CUDA(cudaMemcpyAsync(g->nbr.p + sent, nbr + sent, sizeof(vid_t) * (size_t)(upto - sent),
+                                      cudaMemcpyHostToDevice, st.copy));
+        sent = upto;
+        upto_slot.push_back(upto);
+        ev_chunk.push_back(st.mark());
+    }
+    // library stream: offsets -> validation -> ranking; then range by range
+    GMSB_CUDA(cudaStreamWaitEvent(r.stream, ev_off, 0));
+    k_check_offsets_only<<<grid_for(n, 256), 256, 0, r.stream>>>(g->off.p, n, last, flags.p); launched();
+    GMSB_REQUIRE(flags.get(0) == 0, "graph_from_csr: offsets not monotone or outside the neighbour array");
+    orient_pipeline_begin(*g, pipe);
+    eid_t checked = lo_slot;
+    for (int c = 0; c < chunks; ++c) {
+        GMSB_CUDA(cudaStreamWaitEvent(r.stream, ev_chunk[c], 0));
+        const eid_t upto = upto_slot[c];
+        if (upto > checked) {
+            k_check_slots<<<grid_for(upto - checked, 256), 256, 0, r.stream>>>(g->nbr.p, checked, upto, n, flags.p,
+                                                                              desc.p + 1);
+            launched();
+            checked = upto;
+        }
+        orient_pipeline_range(*g, pipe, cut[c], cut[c + 1]);
+    }
+}
+}  // namespace
+
 Graph *graph_from_csr_host_pipelined(int64_t n, const eid_t *off, const vid_t *nbr) {
     GMSB_REQUIRE(n >= 0 && off != nullptr, "graph_from_csr: bad arguments");
     Runtime &r = rt();
@@ -203,74 +279,17 @@ Graph *graph_from_csr_host_pipelined(int64_t n, const eid_t *off, const vid_t *n
     GMSB_REQUIRE(off[0] == 0 && last >= 0, "graph_from_csr: offsets must start at 0 and be non-negative");
     GMSB_REQUIRE(last == 0 || nbr != nullptr, "graph_from_csr: null neighbour array");
     if (n == 0 || last == 0) return graph_from_csr_device(n, off, nbr, false, true);
-    struct Streams {
-        cudaStream_t copy = nullptr;
-        std::vector<cudaEvent_t> ev;
-        ~Streams() {
-            for (auto e : ev) cudaEventDestroy(e);
-            if (copy) cudaStreamDestroy(copy);
-        }
-    } st;
+    UploadStreams st;
     auto *g = new Graph();
     OrientPipeline pipe;
     try {
         g->n = n; g->slots = last; g->directed = false;
         g->off.alloc(n + 1);
         g->nbr.alloc(last);
-        GMSB_CUDA(cudaStreamCreateWithFlags(&st.copy, cudaStreamNonBlocking));
-        // allocations above may have been served from blocks whose last use is still queued on the library stream
-        GMSB_CUDA(cudaStreamSynchronize(r.stream));
-        auto mark = [&]() {
-            cudaEvent_t e;
-            GMSB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-            st.ev.push_back(e);
-            GMSB_CUDA(cudaEventRecord(e, st.copy));
-            return e;
-        };
-        GMSB_CUDA(cudaMemcpyAsync(g->off.p, off, sizeof(eid_t) * (n + 1), cudaMemcpyHostToDevice, st.copy));
-        cudaEvent_t ev_off = mark();
-        // vertex ranges of about equal slot counts (the host array is only used to pick the cuts: a malformed one is
-        // caught by the device check of the offsets below before any range is processed)
-        constexpr int kChunks = 16;
-        std::vector<int64_t> cut(1, 0);
-        for (int c = 1; c < kChunks; ++c) {
-            const eid_t target = last / kChunks * c;
-            int64_t lo = cut.back(), hi = n;
-            while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (off[mid] < target) lo = mid + 1; else hi = mid; }
-            cut.push_back(lo);
-        }
-        cut.push_back(n);
-        std::vector<cudaEvent_t> ev_chunk;
-        eid_t sent = 0;
-        for (int c = 0; c < kChunks; ++c) {
-            eid_t upto = c + 1 == kChunks ? last : off[cut[c + 1]];
-            if (upto < sent || upto > last) upto = sent;                    // malformed offsets: rejected below
-            if (upto > sent)
-                GMSB_CUDA(cudaMemcpyAsync(g->nbr.p + sent, nbr + sent, sizeof(vid_t) * (size_t)(upto - sent),
-                                          cudaMemcpyHostToDevice, st.copy));
-            sent = upto;
-            ev_chunk.push_back(mark());
-        }
-        // library stream: offsets -> validation -> ranking; then range by range
         DevBuf<int> flags(1);
         DevBuf<unsigned long long> desc(2);
         flags.zero(); desc.zero();
-        GMSB_CUDA(cudaStreamWaitEvent(r.stream, ev_off, 0));
-        k_check_offsets_only<<<grid_for(n, 256), 256, 0, r.stream>>>(g->off.p, n, last, flags.p); launched();
-        GMSB_REQUIRE(flags.get(0) == 0, "graph_from_csr: offsets not monotone or outside the neighbour array");
-        orient_pipeline_begin(*g, pipe);
-        eid_t checked = 0;
-        for (int c = 0; c < kChunks; ++c) {
-            GMSB_CUDA(cudaStreamWaitEvent(r.stream, ev_chunk[c], 0));
-            const eid_t upto = c + 1 == kChunks ? last : off[cut[c + 1]];
-            if (upto > checked) {
-                k_check_slots<<<grid_for(upto - checked, 256), 256, 0, r.stream>>>(g->nbr.p, checked, upto, n, flags.p,
-                                                                                  desc.p + 1);
-                launched();
-                checked = upto;
-            }
-            orient_pipeline_range(*g, pipe, cut[c], cut[c + 1]);
-        }
+        upload_and_orient_range(g, pipe, st, off, nbr, 0, n, 16, flags, desc);
         k_check_offsets<<<grid_for(n, 256), 256, 0, r.stream>>>(g->off.p, g->nbr.p, n, last, flags.p, desc.p); launched();
         unsigned long long h[2];
         desc.download(h, 2);
@@ -293,6 +312,81 @@ Graph *graph_from_csr_host_pipelined(int64_t n, const eid_t *off, const vid_t *n
         delete g;
         throw;
     }
+    return g;
+}
+
+// ---- sharded construction (one process per device) ----------------------------------------------------------------------
+// Device `part` of `parts` uploads the offsets and the neighbour slots of ITS vertex range only (ranges of about equal
+// slot counts, computed the same way by everyone from the host offsets), orients and sorts those rows, and packs them
+// into a piece.  The caller exchanges the pieces (one all-gather) and the d+ values (one all-reduce of an int32[n] that
+// every device filled in its own range); shard_finish then moves all rows into rank order.  Per device the host link
+// carries 1/parts of the neighbour array and the orientation passes touch 1/parts of the rows.  The resulting handle
+// holds the oriented representation only (Graph::dag_only): the symmetric lists of the other ranges never arrive.
+Shard::~Shard() { delete d; delete g; }
+
+Shard *shard_begin(int64_t n, const eid_t *off, const vid_t *nbr, int part, int parts, int64_t *piece_len) {
+    GMSB_REQUIRE(n >= 0 && off != nullptr && piece_len != nullptr, "shard_begin: bad arguments");
+    GMSB_REQUIRE(parts >= 1 && parts <= 64 && part >= 0 && part < parts, "shard_begin: bad partition");
+    Runtime &r = rt();
+    const eid_t last = off[n];
+    GMSB_REQUIRE(off[0] == 0 && last >= 0, "graph_from_csr: offsets must start at 0 and be non-negative");
+    GMSB_REQUIRE(last == 0 || nbr != nullptr, "graph_from_csr: null neighbour array");
+    auto *s = new Shard();
+    UploadStreams st;
+    OrientPipeline pipe;
+    try {
+        s->part = part; s->parts = parts;
+        s->cut.assign((size_t)parts + 1, n);
+        s->cut[0] = 0;
+        for (int i = 1; i < parts; ++i) {           // first vertex whose list starts at or after slot last / parts * i
+            const eid_t target = last / parts * i;
+            int64_t lo = s->cut[(size_t)i - 1], hi = n;
+            while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (off[mid] < target) lo = mid + 1; else hi = mid; }
+            s->cut[(size_t)i] = lo;
+        }
+        const int64_t u0 = s->cut[(size_t)part], u1 = s->cut[(size_t)part + 1];
+        Graph *g = s->g = new Graph();
+        g->n = n; g->slots = last; g->directed = false; g->dag_only = true;
+        g->off.alloc(n + 1);
+        g->nbr.alloc(last);                 // only the slots of [u0, u1) are ever filled
+        DevBuf<int> flags(1);
+        DevBuf<unsigned long long> desc(2);
+        flags.zero(); desc.zero();
+        upload_and_orient_range(g, pipe, st, off, nbr, u0, u1, 4, flags, desc);
+        s->d = pipe.d;
+        pipe.d = nullptr;
+        GMSB_REQUIRE(flags.get(0) == 0, "graph_from_csr: neighbour id out of range");
+        s->piece_len = orient_piece_layout(*g, s->d->rank.p, pipe.w, u0, u1, s->piece_off);
+        s->w = std::move(pipe.w);
+        *piece_len = s->piece_len;
+        GMSB_CUDA(cudaStreamSynchronize(r.stream));
+    } catch (...) {
+        cudaStreamSynchronize(st.copy);
+        cudaStreamSynchronize(r.stream);
+        delete pipe.d;
+        delete s;
+        throw;
+    }
+    return s;
+}
+
+void shard_export(Shard &s, vid_t *piece_dev, int32_t *dplus_all_dev) {
+    GMSB_REQUIRE(dplus_all_dev != nullptr && (piece_dev != nullptr || s.piece_len == 0), "shard_export: null buffer");
+    GMSB_REQUIRE(s.g != nullptr && s.d != nullptr, "shard_export: the shard has been finished");
+    orient_piece_export(*s.g, s.w, s.cut[(size_t)s.part], s.cut[(size_t)s.part + 1], s.piece_off, piece_dev, dplus_all_dev);
+}
+
+Graph *shard_finish(Shard &s, const vid_t *pieces_dev, int64_t piece_stride, const int32_t *dplus_all_dev) {
+    GMSB_REQUIRE(s.g != nullptr && s.d != nullptr, "shard_finish: the shard has been finished");
+    GMSB_REQUIRE(dplus_all_dev != nullptr && piece_stride >= s.piece_len, "shard_finish: bad arguments");
+    s.w = OrientRows();                     // the work buffers of the own range are no longer needed
+    s.g->nbr.release();
+    dag_from_pieces(*s.d, dplus_all_dev, pieces_dev, piece_stride, s.cut.data(), s.parts);
+    Graph *g = s.g;
+    g->dag = s.d;
+    g->dag_pinned = true;
+    s.g = nullptr;
+    s.d = nullptr;
     return g;
 }
 

@@ -39,22 +39,6 @@ __global__ void k_rank_from_order(const vid_t *__restrict__ order, int64_t n, vi
         rank[order[i]] = (vid_t)i;
 }
 
-// One warp per vertex: d+(u) = |{ v in N(u) : rank[v] > rank[u] }|, stored at cnt[rank[u] + 1].
-__global__ void k_count_out(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, int64_t n,
-                            const vid_t *__restrict__ rank, eid_t *__restrict__ cnt) {
-    int lane = threadIdx.x & 31;
-    int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t u = warp; u < n; u += nwarps) {
-        eid_t b = off[u], e = off[u + 1];
-        vid_t ru = rank[u];
-        int c = 0;
-        for (eid_t s = b + lane; s < e; s += 32) c += rank[nbr[s]] > ru;
-        for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-        if (lane == 0) cnt[ru + 1] = c;
-    }
-}
-
 // One warp per vertex: write (rank[u]<<32 | rank[v]) for the kept slots, compacted with ballots, into the
 // segment of rank[u]; the order inside a segment is fixed afterwards by the radix sort.
 __global__ void k_emit_out(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, int64_t n,
@@ -169,12 +153,14 @@ __device__ __forceinline__ unsigned window_mask(int rel, int deg, int i0) {
 }
 
 // (1) relabel + count: rnbr[s] = rank[nbr[s]] is stored so that the emit pass streams instead of gathering again;
-// d+(u) goes to cnt[rank[u] + 1].  Vertices with a big list are queued (bigq) for k_relabel_big.
+// d+(u) goes to dold[u] (indexed by the ORIGINAL id: every pass up to the final row move works on vertex ranges of the
+// input, so that ranges can be processed as they arrive from the host, or by different devices).  Vertices with a big
+// list are queued (bigq) for k_relabel_big.
 // (The pass runs over the vertex range [u_begin, n): the upload pipeline calls it range by range; ids are bounds-checked
 // here because in that pipeline the validation of a range is only enqueued, not yet read back, when this runs.)
 __global__ void __launch_bounds__(256)
 k_relabel_count(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, int64_t u_begin, int64_t n, int64_t n_all,
-                const vid_t *__restrict__ rank, vid_t *__restrict__ rnbr, eid_t *__restrict__ cnt,
+                const vid_t *__restrict__ rank, vid_t *__restrict__ rnbr, int32_t *__restrict__ dold,
                 vid_t *__restrict__ bigq, int *__restrict__ nbigq) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -202,14 +188,14 @@ k_relabel_count(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, in
         }
         if (u < n) {
             if (ck.big) bigq[atomicAdd(nbigq, 1)] = (vid_t)u;
-            else cnt[ru + 1] = c;
+            else dold[u] = c;
         }
     }
 }
-// big lists: blockIdx.x = queue entry, blockIdx.y = one of gridDim.y interleaved parts of the list
+// big lists: blockIdx.x = queue entry, blockIdx.y = one of gridDim.y interleaved parts of the list (dold starts at 0)
 __global__ void __launch_bounds__(256)
 k_relabel_big(const vid_t *__restrict__ bigq, const eid_t *__restrict__ off, const vid_t *__restrict__ nbr,
-              const vid_t *__restrict__ rank, vid_t *__restrict__ rnbr, eid_t *__restrict__ cnt, int64_t n_all) {
+              const vid_t *__restrict__ rank, vid_t *__restrict__ rnbr, int32_t *__restrict__ dold, int64_t n_all) {
     const vid_t u = bigq[blockIdx.x];
     const eid_t b = off[u], e = off[u + 1];
     const vid_t ru = rank[u];
@@ -221,7 +207,7 @@ k_relabel_big(const vid_t *__restrict__ bigq, const eid_t *__restrict__ off, con
         c += rv > ru;
     }
     for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if ((threadIdx.x & 31) == 0 && c) atomicAdd(reinterpret_cast<unsigned long long *>(&cnt[ru + 1]), (unsigned long long)c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&dold[u], c);
 }
 
 __device__ __forceinline__ vid_t warp_bitonic_sort(vid_t v, int lane) {
@@ -237,24 +223,30 @@ __device__ __forceinline__ vid_t warp_bitonic_sort(vid_t v, int lane) {
     return v;
 }
 
-// (2) emit: the chunk's higher-ranked neighbours are compacted with ballots.  Lists of <= kLaneSortMax survivors are
-// staged in the warp's shared-memory slice, sorted there by their owner lane (insertion sort: 32 lists at once) and
-// written in final order; longer ones are written unsorted and queued for the warp / CTA sorters.
+// (2) emit: the chunk's higher-ranked neighbours are compacted with ballots into the FRONT OF THE ROW'S OWN SLOT RANGE of
+// a second slots-sized array (row u of the symmetric CSR starts at off[u]; its d+(u) survivors land at
+// trow[off[u] .. off[u] + d+(u))), so the pass needs nothing from outside its vertex range — no offsets of the
+// oriented graph, which exist only once every vertex has been counted.  Lists of <= kLaneSortMax survivors are staged in
+// the warp's shared-memory slice, sorted there by their owner lane (insertion sort: 32 lists at once) and written in
+// final order; longer ones are written unsorted and queued for the warp / CTA sorters as (start << 24 | length).
+constexpr int kQLenBits = 24;
+constexpr uint64_t kQLenMask = (1ull << kQLenBits) - 1ull;
 __global__ void __launch_bounds__(256)
-k_emit_sorted(const eid_t *__restrict__ off, const vid_t *__restrict__ rnbr, int64_t n, const vid_t *__restrict__ rank,
-              const eid_t *__restrict__ doff, vid_t *__restrict__ dnbr, vid_t *__restrict__ big, int *__restrict__ nbig) {
+k_emit_rows(const eid_t *__restrict__ off, const vid_t *__restrict__ rnbr, int64_t u_begin, int64_t n,
+            const vid_t *__restrict__ rank, const int32_t *__restrict__ dold, vid_t *__restrict__ trow,
+            uint64_t *__restrict__ queue, int64_t qcap, int *__restrict__ nq) {
     __shared__ vid_t stage_s[8][32 * kLaneSortMax];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     vid_t *stage = stage_s[wib];
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t u0 = warp * 32; u0 < n; u0 += nwarps * 32) {
+    for (int64_t u0 = u_begin + warp * 32; u0 < n; u0 += nwarps * 32) {
         const WarpChunk ck = load_chunk(off, u0, n, lane);
         const int64_t u = u0 + lane;
         const bool mine = u < n && !ck.big;
         const vid_t ru = u < n ? rank[u] : 0;
-        const eid_t ob = mine ? doff[ru] : 0;
-        const int c = mine ? (int)(doff[ru + 1] - ob) : 0;
+        const eid_t ob = ck.abs;                                     // the row's survivors start where the row starts
+        const int c = mine ? dold[u] : 0;
         const bool small = c <= kLaneSortMax;
         const int sc = small ? c : 0;
         int sincl = sc;
@@ -272,7 +264,8 @@ k_emit_sorted(const eid_t *__restrict__ off, const vid_t *__restrict__ rnbr, int
             const bool act = i < ck.total;
             const int owner = chunk_owner(ck.rel, act ? i : ck.total - 1);
             const int orel = __shfl_sync(0xffffffffu, ck.rel, owner);
-            const eid_t s = __shfl_sync(0xffffffffu, ck.abs, owner) + (i - orel);
+            const eid_t oob = __shfl_sync(0xffffffffu, ob, owner);
+            const eid_t s = oob + (i - orel);
             const vid_t ro = __shfl_sync(0xffffffffu, ru, owner);
             const vid_t rv = act ? rnbr[s] : -1;
             const bool kp = act && rv > ro;
@@ -282,9 +275,8 @@ k_emit_sorted(const eid_t *__restrict__ off, const vid_t *__restrict__ rnbr, int
             const int pos = __shfl_sync(0xffffffffu, w, owner) + before;
             const bool osmall = __shfl_sync(0xffffffffu, (int)small, owner) != 0;
             const int osp = __shfl_sync(0xffffffffu, sp, owner);
-            const eid_t oob = __shfl_sync(0xffffffffu, ob, owner);
             if (kp) {
-                if (osmall) stage[osp + pos] = rv; else dnbr[oob + pos] = rv;
+                if (osmall) stage[osp + pos] = rv; else trow[oob + pos] = rv;
             }
             w += __popc(kept & window_mask(ck.rel, ck.deg, i0));
         }
@@ -304,24 +296,24 @@ k_emit_sorted(const eid_t *__restrict__ off, const vid_t *__restrict__ rnbr, int
             const int owner = chunk_owner(sp, act ? i : nstaged - 1);
             const eid_t oob = __shfl_sync(0xffffffffu, ob, owner);
             const int osp = __shfl_sync(0xffffffffu, sp, owner);
-            if (act) dnbr[oob + (i - osp)] = stage[i];
+            if (act) trow[oob + (i - osp)] = stage[i];
         }
         if (mine && !small) {
-            // two queues filled from opposite ends of one array: [0, nbig[0]) mid-size lists, (n-1-nbig[1], n-1] long
-            if (c <= 512) big[atomicAdd(&nbig[0], 1)] = ru;
-            else big[n - 1 - atomicAdd(&nbig[1], 1)] = ru;
+            // two queues filled from opposite ends of one array: [0, nq[0]) mid-size lists, (qcap-1-nq[1], qcap-1] long
+            const uint64_t entry = ((uint64_t)ob << kQLenBits) | (uint64_t)c;
+            if (c <= 512) queue[atomicAdd(&nq[0], 1)] = entry;
+            else queue[qcap - 1 - atomicAdd(&nq[1], 1)] = entry;
         }
     }
 }
 // big lists: survivors appended through one cursor per list (unsorted; the sorters fix the order)
 __global__ void __launch_bounds__(256)
 k_emit_big(const vid_t *__restrict__ bigq, const eid_t *__restrict__ off, const vid_t *__restrict__ rnbr,
-           const vid_t *__restrict__ rank, const eid_t *__restrict__ doff, vid_t *__restrict__ dnbr,
-           int *__restrict__ cursor, int64_t n, vid_t *__restrict__ big, int *__restrict__ nbig) {
+           const vid_t *__restrict__ rank, const int32_t *__restrict__ dold, vid_t *__restrict__ trow,
+           int *__restrict__ cursor, uint64_t *__restrict__ queue, int64_t qcap, int *__restrict__ nq) {
     const vid_t u = bigq[blockIdx.x];
     const eid_t b = off[u], e = off[u + 1];
     const vid_t ru = rank[u];
-    const eid_t ob = doff[ru];
     const int lane = threadIdx.x & 31;
     const eid_t first = b + (eid_t)blockIdx.y * blockDim.x, stride = (eid_t)gridDim.y * blockDim.x;
     for (eid_t s0 = first; s0 < e; s0 += stride) {                  // s0 is uniform over the CTA
@@ -332,35 +324,42 @@ k_emit_big(const vid_t *__restrict__ bigq, const eid_t *__restrict__ off, const 
         int base = 0;
         if (lane == 0 && kept) base = atomicAdd(&cursor[blockIdx.x], __popc(kept));
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (kp) dnbr[ob + base + __popc(kept & ((1u << lane) - 1u))] = rv;
+        if (kp) trow[b + base + __popc(kept & ((1u << lane) - 1u))] = rv;
     }
     if (blockIdx.y == 0 && threadIdx.x == 0) {
-        const int c = (int)(doff[ru + 1] - ob);
+        const int c = dold[u];
         if (c > 1) {
-            if (c <= 512) big[atomicAdd(&nbig[0], 1)] = ru;
-            else big[n - 1 - atomicAdd(&nbig[1], 1)] = ru;
+            const uint64_t entry = ((uint64_t)b << kQLenBits) | (uint64_t)c;
+            if (c <= 512) queue[atomicAdd(&nq[0], 1)] = entry;
+            else queue[qcap - 1 - atomicAdd(&nq[1], 1)] = entry;
         }
     }
 }
 
-// (3a) warp sorter for queued lists of 33..kWarpSortCap elements: one warp per list, bitonic network in the warp's
-// own shared-memory slice (no block barriers), eight lists per CTA in flight.
+// (3a) warp sorter for queued lists of up to kWarpSortCap elements: one warp per list; up to 32 elements in registers
+// (shuffle network), longer ones as a bitonic network in the warp's own shared-memory slice (no block barriers), eight
+// lists per CTA in flight.
 constexpr int kWarpSortCap = 512;
 __global__ void __launch_bounds__(256)
-k_sort_mid(const vid_t *__restrict__ big, int nbig, const eid_t *__restrict__ doff, vid_t *__restrict__ dnbr) {
+k_sort_mid(const uint64_t *__restrict__ queue, int nlists, vid_t *__restrict__ rows) {
     __shared__ vid_t bufs[8][kWarpSortCap];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     vid_t *buf = bufs[wib];
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < nbig; t += nwarps) {
-        const vid_t ru = big[t];
-        const eid_t ob = doff[ru];
-        const int c = (int)(doff[ru + 1] - ob);
+    for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < nlists; t += nwarps) {
+        const uint64_t entry = queue[t];
+        const eid_t ob = (eid_t)(entry >> kQLenBits);
+        const int c = (int)(entry & kQLenMask);
         if (c > kWarpSortCap) continue;                    // left to the CTA sorter
+        if (c <= 32) {
+            const vid_t v = warp_bitonic_sort(lane < c ? rows[ob + lane] : 0x7fffffff, lane);
+            if (lane < c) rows[ob + lane] = v;
+            continue;
+        }
         int P = 64;
         while (P < c) P <<= 1;
         __syncwarp();
-        for (int i = lane; i < P; i += 32) buf[i] = i < c ? dnbr[ob + i] : 0x7fffffff;
+        for (int i = lane; i < P; i += 32) buf[i] = i < c ? rows[ob + i] : 0x7fffffff;
         __syncwarp();
         for (int k = 2; k <= P; k <<= 1) {
             for (int j = k >> 1; j > 0; j >>= 1) {
@@ -375,24 +374,24 @@ k_sort_mid(const vid_t *__restrict__ big, int nbig, const eid_t *__restrict__ do
                 __syncwarp();
             }
         }
-        for (int i = lane; i < c; i += 32) dnbr[ob + i] = buf[i];
+        for (int i = lane; i < c; i += 32) rows[ob + i] = buf[i];
     }
 }
 
-// (3b) CTA sorter for the few longer lists: bitonic network in shared memory, sized per list.
+// (3b) CTA sorter for the few longer lists: bitonic network in shared memory (kSortCap elements).
 constexpr int kSortCap = 8192;
 __global__ void __launch_bounds__(256)
-k_sort_big(const vid_t *__restrict__ big, int nbig, const eid_t *__restrict__ doff, vid_t *__restrict__ dnbr) {
+k_sort_big(const uint64_t *__restrict__ queue, int nlists, vid_t *__restrict__ rows) {
     extern __shared__ vid_t buf[];
-    for (int t = blockIdx.x; t < nbig; t += gridDim.x) {
-        const vid_t ru = big[t];
-        const eid_t ob = doff[ru];
-        const int c = (int)(doff[ru + 1] - ob);
-        if (c <= kWarpSortCap) continue;                   // done by the warp sorter
+    for (int t = blockIdx.x; t < nlists; t += gridDim.x) {
+        const uint64_t entry = queue[t];
+        const eid_t ob = (eid_t)(entry >> kQLenBits);
+        const int c = (int)(entry & kQLenMask);
+        if (c <= kWarpSortCap || c > kSortCap) continue;   // done by the warp sorter / left to the radix-sort fallback
         int P = 64;
         while (P < c) P <<= 1;
         __syncthreads();
-        for (int i = threadIdx.x; i < P; i += blockDim.x) buf[i] = i < c ? dnbr[ob + i] : 0x7fffffff;
+        for (int i = threadIdx.x; i < P; i += blockDim.x) buf[i] = i < c ? rows[ob + i] : 0x7fffffff;
         __syncthreads();
         for (int k = 2; k <= P; k <<= 1) {
             for (int j = k >> 1; j > 0; j >>= 1) {
@@ -407,8 +406,74 @@ k_sort_big(const vid_t *__restrict__ big, int nbig, const eid_t *__restrict__ do
                 __syncthreads();
             }
         }
-        for (int i = threadIdx.x; i < c; i += blockDim.x) dnbr[ob + i] = buf[i];
+        for (int i = threadIdx.x; i < c; i += blockDim.x) rows[ob + i] = buf[i];
     }
+}
+
+// (4) offsets of the oriented graph: d+ scattered from original-id order to rank order (an inclusive scan follows)
+__global__ void k_counts_by_rank(const int32_t *__restrict__ dold, const vid_t *__restrict__ rank, int64_t n,
+                                 eid_t *__restrict__ cnt /* n+1, [0] = 0 */) {
+    for (int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; u < n; u += (int64_t)gridDim.x * blockDim.x)
+        cnt[rank[u] + 1] = (eid_t)dold[u];
+    if (blockIdx.x == 0 && threadIdx.x == 0) cnt[0] = 0;
+}
+
+// (5) row move: the len[u] elements at src[src_start[u] ..) go to dst[dst_start ..) for every vertex u of the range,
+// where dst_start = dst_off[rank[u]] (BY_RANK: rows into their place in the oriented CSR) or dst_off[u - u_begin] (rows
+// packed in original-id order: the piece a device hands to the others).  Warp chunks as above: 32 rows per warp, their
+// elements streamed 32 at a time.
+template <bool BY_RANK>
+__global__ void __launch_bounds__(256)
+k_move_rows(const eid_t *__restrict__ src_start, const int32_t *__restrict__ len, const vid_t *__restrict__ src,
+            int64_t u_begin, int64_t u_end, const eid_t *__restrict__ dst_off, const vid_t *__restrict__ rank,
+            vid_t *__restrict__ dst) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t u0 = u_begin + warp * 32; u0 < u_end; u0 += nwarps * 32) {
+        const int64_t u = u0 + lane;
+        const bool valid = u < u_end;
+        const int c = valid ? len[u] : 0;
+        const eid_t ss = valid ? src_start[u] : 0;
+        const eid_t dd = valid ? dst_off[BY_RANK ? (int64_t)rank[u] : u - u_begin] : 0;
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int x = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += x;
+        }
+        const int rel = incl - c;
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        for (int i0 = 0; i0 < total; i0 += 32) {
+            const int i = i0 + lane;
+            const bool act = i < total;
+            const int owner = chunk_owner(rel, act ? i : total - 1);
+            const int j = i - __shfl_sync(0xffffffffu, rel, owner);
+            const eid_t so = __shfl_sync(0xffffffffu, ss, owner), dofs = __shfl_sync(0xffffffffu, dd, owner);
+            if (act) dst[dofs + j] = src[so + j];
+        }
+    }
+}
+
+// where vertex u's row sits in the gathered pieces of a sharded build: piece r holds the rows of the original ids
+// [cut[r], cut[r+1]) packed in that order and starts at r * stride; scan = exclusive scan of d+ in original-id order
+constexpr int kMaxParts = 64;
+struct PartCuts { int64_t cut[kMaxParts + 1]; int parts; };
+__global__ void k_piece_starts(const eid_t *__restrict__ scan, int64_t n, PartCuts pc, int64_t stride,
+                               eid_t *__restrict__ src_start) {
+    for (int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; u < n; u += (int64_t)gridDim.x * blockDim.x) {
+        int r = 0;
+        while (r + 1 < pc.parts && u >= pc.cut[r + 1]) ++r;
+        src_start[u] = scan[u] - scan[pc.cut[r]] + (eid_t)r * stride;
+    }
+}
+
+__global__ void k_max_i32(const int32_t *__restrict__ a, int64_t n, int *out) {
+    int mx = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        mx = max(mx, a[i]);
+    for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0 && mx) atomicMax(out, mx);
 }
 
 }  // namespace
@@ -440,80 +505,127 @@ void degree_order(const Graph &g, DevBuf<vid_t> &order, DevBuf<vid_t> &rank, int
 
 constexpr int kBigParts = 32;                  // CTAs per big list
 
-// stage 1 of orient_by_rank over the vertex range [u_begin, u_end): needs the offsets and the slots of the range
-static void relabel_stage(const Graph &g, const vid_t *rank_dev, vid_t *rnbr, eid_t *doff, vid_t *bigq, int *nbigq,
-                          int64_t u_begin, int64_t u_end) {
+// ---- host side of the row-local orientation ---------------------------------------------------------------------------
+// The passes are driven in three ways: over the whole graph at once (build_degree_dag, induce_directed), vertex range by
+// vertex range while the host arrays are still uploading (graph_build.cu), and over one vertex range per device with the
+// finished rows exchanged between the devices (shard_*).
+void orient_rows_begin(const Graph &g, OrientRows &w) {
+    w.rnbr.alloc(g.slots);
+    w.trow.alloc(g.slots);
+    w.dold.alloc(g.n + 1);                      // one spare entry: scans over a range read one element past it
+    w.dold.zero();
+    w.bigq.alloc(g.n);
+    w.queue.alloc(g.n);                         // at most one entry per vertex
+    w.counters.alloc(3);                        // [0] big lists queued  [1] mid sort queue  [2] long sort queue
+    w.counters.zero();
+    w.big_done = w.sorted_mid = w.sorted_long = 0;
+}
+
+// passes (1) + (2) over the vertex range [u_begin, u_end): needs the offsets and the neighbour slots of the range
+void orient_rows_range(const Graph &g, const vid_t *rank_dev, OrientRows &w, int64_t u_begin, int64_t u_end) {
     Runtime &r = rt();
     if (u_end <= u_begin) return;
-    k_relabel_count<<<grid_for(u_end - u_begin, 256), 256, 0, r.stream>>>(g.off.p, g.nbr.p, u_begin, u_end, g.n, rank_dev,
-                                                                        rnbr, doff, bigq, nbigq);
+    const int grid = grid_for(u_end - u_begin, 256);
+    k_relabel_count<<<grid, 256, 0, r.stream>>>(g.off.p, g.nbr.p, u_begin, u_end, g.n, rank_dev, w.rnbr.p, w.dold.p,
+                                                w.bigq.p, w.counters.p);
+    launched();
+    k_emit_rows<<<grid, 256, 0, r.stream>>>(g.off.p, w.rnbr.p, u_begin, u_end, rank_dev, w.dold.p, w.trow.p, w.queue.p,
+                                            (int64_t)w.queue.n, w.counters.p + 1);
     launched();
 }
 
-// stage 2: big lists, offsets, emit + sort
-static void finish_stage(const Graph &g, const vid_t *rank_dev, DevBuf<vid_t> &rnbr, DevBuf<vid_t> &bigq,
-                         DevBuf<int> &nbigq, DevBuf<eid_t> &doff, DevBuf<vid_t> &dnbr, int64_t *m_out, int *max_dplus,
-                         DevBuf<int32_t> *dplus, PhaseTrace &tr) {
+// lists of more than kBigList slots queued since the last call: many CTAs per list
+void orient_rows_big(const Graph &g, const vid_t *rank_dev, OrientRows &w) {
     Runtime &r = rt();
-    const int64_t n = g.n;
-    int n_bigq = 0;
-    if (n) {
-        n_bigq = nbigq.get(0);
-        if (n_bigq) {
-            k_relabel_big<<<dim3((unsigned)n_bigq, kBigParts), 256, 0, r.stream>>>(bigq.p, g.off.p, g.nbr.p, rank_dev,
-                                                                                 rnbr.p, doff.p, n);
-            launched();
-        }
-        inclusive_sum_inplace(doff.p, n + 1);
+    if (g.n == 0) return;
+    const int queued = w.counters.get(0);
+    const int fresh = queued - w.big_done;
+    if (fresh <= 0) return;
+    const vid_t *q = w.bigq.p + w.big_done;
+    k_relabel_big<<<dim3((unsigned)fresh, kBigParts), 256, 0, r.stream>>>(q, g.off.p, g.nbr.p, rank_dev, w.rnbr.p,
+                                                                         w.dold.p, g.n);
+    launched();
+    DevBuf<int> cursor(fresh);
+    cursor.zero();
+    k_emit_big<<<dim3((unsigned)fresh, kBigParts), 256, 0, r.stream>>>(q, g.off.p, w.rnbr.p, rank_dev, w.dold.p, w.trow.p,
+                                                                      cursor.p, w.queue.p, (int64_t)w.queue.n,
+                                                                      w.counters.p + 1);
+    launched();
+    GMSB_CUDA(cudaStreamSynchronize(r.stream));     // cursor is released at the end of this scope
+    w.big_done = queued;
+}
+
+// sorts the lists queued since the last call (reads the queue counters back: a host synchronisation)
+void orient_rows_sort(OrientRows &w) {
+    Runtime &r = rt();
+    if (w.queue.n == 0) return;
+    static_assert(kWarpSortCap == 512, "the emit kernels split their queues at 512");
+    int h[3];
+    w.counters.download(h, 3);
+    const int mid = h[1] - w.sorted_mid, lng = h[2] - w.sorted_long;
+    if (mid > 0) {
+        const int grid = (int)std::min<int64_t>(ceil_div(mid, 8), (int64_t)r.sm_count * 12);
+        k_sort_mid<<<grid, 256, 0, r.stream>>>(w.queue.p + w.sorted_mid, mid, w.trow.p); launched();
     }
-    tr.mark("orient: relabel + count");
-    int64_t m = n ? doff.get(n) : 0;
-    *m_out = m;
-    dnbr.alloc(m);
+    if (lng > 0) {              // the long queue grows downwards from the end of the array
+        const int grid = (int)std::min<int64_t>(lng, (int64_t)r.sm_count * 6);
+        k_sort_big<<<grid, 256, (size_t)kSortCap * sizeof(vid_t), r.stream>>>(w.queue.p + (w.queue.n - (size_t)h[2]), lng,
+                                                                             w.trow.p);
+        launched();
+    }
+    w.sorted_mid = h[1];
+    w.sorted_long = h[2];
+}
+
+// offsets of the oriented graph (rank order) from d+ in original-id order
+static void offsets_by_rank(int64_t n, const int32_t *dold, const vid_t *rank_dev, DevBuf<eid_t> &doff, int64_t *m_out,
+                            int *max_dplus, DevBuf<int32_t> *dplus) {
+    Runtime &r = rt();
+    doff.alloc(n + 1);
     int maxd = 0;
-    if (n) {
+    int64_t m = 0;
+    if (n == 0) doff.zero();
+    else {
+        k_counts_by_rank<<<grid_for(n, 256), 256, 0, r.stream>>>(dold, rank_dev, n, doff.p); launched();
+        inclusive_sum_inplace(doff.p, n + 1);
+        m = doff.get(n);
         DevBuf<int> mx(1);
         mx.zero();
         if (dplus) dplus->alloc(n);
         k_max_deg<<<grid_for(n, 256), 256, 0, r.stream>>>(doff.p, n, mx.p, dplus ? dplus->p : nullptr); launched();
         maxd = mx.get(0);
     }
+    *m_out = m;
     if (max_dplus) *max_dplus = maxd;
-    if (m == 0) return;
+}
+
+static int on_chip_sort_cap() {
     int cap = kSortCap;
     if (const char *env = getenv("GMSB_ORIENT_SORT_CAP")) cap = std::min(kSortCap, std::max(0, atoi(env)));   // tests
-    if (maxd <= cap) {
-        // lists sorted on chip: registers (<= 32) or shared memory; one streaming pass in, one out
-        static_assert(kWarpSortCap == 512, "k_emit_sorted splits its queues at 512");
-        DevBuf<vid_t> big(n);
-        DevBuf<int> nbig(2);
-        nbig.zero();
-        k_emit_sorted<<<grid_for(n, 256), 256, 0, r.stream>>>(g.off.p, rnbr.p, n, rank_dev, doff.p, dnbr.p, big.p,
-                                                             nbig.p);
-        launched();
-        if (n_bigq) {
-            DevBuf<int> cursor(n_bigq);
-            cursor.zero();
-            k_emit_big<<<dim3((unsigned)n_bigq, kBigParts), 256, 0, r.stream>>>(bigq.p, g.off.p, rnbr.p, rank_dev, doff.p,
-                                                                              dnbr.p, cursor.p, n, big.p, nbig.p);
-            launched();
-            GMSB_CUDA(cudaStreamSynchronize(r.stream));     // cursor is released at the end of this scope
-        }
-        tr.mark("orient: emit");
-        int h_nb[2];
-        nbig.download(h_nb, 2);
-        if (h_nb[0]) {
-            const int grid = (int)std::min<int64_t>(ceil_div(h_nb[0], 8), (int64_t)r.sm_count * 12);
-            k_sort_mid<<<grid, 256, 0, r.stream>>>(big.p, h_nb[0], doff.p, dnbr.p); launched();
-        }
-        if (h_nb[1]) {
-            int P = 64;
-            while (P < maxd) P <<= 1;
-            const int grid = (int)std::min<int64_t>(h_nb[1], (int64_t)r.sm_count * 8);
-            k_sort_big<<<grid, 256, (size_t)P * sizeof(vid_t), r.stream>>>(big.p + (n - h_nb[1]), h_nb[1], doff.p, dnbr.p);
-            launched();
-        }
+    return cap;
+}
+
+// every range has been through orient_rows_range: big lists, offsets, remaining sorts, rows into rank order
+void orient_rows_finish(const Graph &g, const vid_t *rank_dev, OrientRows &w, DevBuf<eid_t> &doff, DevBuf<vid_t> &dnbr,
+                        int64_t *m_out, int *max_dplus, DevBuf<int32_t> *dplus, PhaseTrace &tr) {
+    Runtime &r = rt();
+    const int64_t n = g.n;
+    orient_rows_big(g, rank_dev, w);
+    int maxd = 0;
+    offsets_by_rank(n, w.dold.p, rank_dev, doff, m_out, &maxd, dplus);
+    if (max_dplus) *max_dplus = maxd;
+    const int64_t m = *m_out;
+    tr.mark("orient: relabel + count + emit");
+    dnbr.alloc(m);
+    if (m == 0) return;
+    if (maxd <= on_chip_sort_cap()) {
+        // lists sorted on chip: registers (<= 32) or shared memory; then one streaming pass moves the rows into place
+        orient_rows_sort(w);
         tr.mark("orient: list sorts");
+        k_move_rows<true><<<grid_for(n, 256), 256, 0, r.stream>>>(g.off.p, w.dold.p, w.trow.p, 0, n, doff.p, rank_dev,
+                                                                 dnbr.p);
+        launched();
+        tr.mark("orient: rows into rank order");
     } else {
         // general fallback for lists longer than the on-chip sorter: one global radix sort of (rank[u], rank[v]) keys
         DevBuf<uint64_t> keys(m), alt(m);
@@ -526,15 +638,12 @@ static void finish_stage(const Graph &g, const vid_t *rank_dev, DevBuf<vid_t> &r
 
 void orient_by_rank(const Graph &g, const vid_t *rank_dev, DevBuf<eid_t> &doff, DevBuf<vid_t> &dnbr, int64_t *m_out,
                     int *max_dplus, DevBuf<int32_t> *dplus) {
-    const int64_t n = g.n;
     PhaseTrace tr("GMSB_TC_TRACE");
-    doff.alloc(n + 1);
-    doff.zero();
-    DevBuf<vid_t> rnbr(g.slots), bigq(n);
-    DevBuf<int> nbigq(1);
-    nbigq.zero();
-    relabel_stage(g, rank_dev, rnbr.p, doff.p, bigq.p, nbigq.p, 0, n);
-    finish_stage(g, rank_dev, rnbr, bigq, nbigq, doff, dnbr, m_out, max_dplus, dplus, tr);
+    OrientRows w;
+    orient_rows_begin(g, w);
+    orient_rows_range(g, rank_dev, w, 0, g.n);
+    orient_rows_finish(g, rank_dev, w, doff, dnbr, m_out, max_dplus, dplus, tr);
+    GMSB_CUDA(cudaStreamSynchronize(rt().stream));      // the work buffers are released when this returns
 }
 
 void orient_pipeline_begin(const Graph &g, OrientPipeline &p) {
@@ -542,20 +651,69 @@ void orient_pipeline_begin(const Graph &g, OrientPipeline &p) {
     p.d = new Dag();
     p.d->n = g.n;
     degree_order(g, p.d->order, p.d->rank, &p.d->max_deg);
-    p.d->off.alloc(g.n + 1);
-    p.d->off.zero();
-    p.rnbr.alloc(g.slots);
-    p.bigq.alloc(g.n);
-    p.nbigq.alloc(1);
-    p.nbigq.zero();
+    orient_rows_begin(g, p.w);
 }
 void orient_pipeline_range(const Graph &g, OrientPipeline &p, int64_t u_begin, int64_t u_end) {
-    relabel_stage(g, p.d->rank.p, p.rnbr.p, p.d->off.p, p.bigq.p, p.nbigq.p, u_begin, u_end);
+    orient_rows_range(g, p.d->rank.p, p.w, u_begin, u_end);
+    orient_rows_sort(p.w);          // the range's lists are sorted while the next range is still on its way
 }
 void orient_pipeline_finish(const Graph &g, OrientPipeline &p) {
     PhaseTrace tr("GMSB_TC_TRACE");
-    finish_stage(g, p.d->rank.p, p.rnbr, p.bigq, p.nbigq, p.d->off, p.d->nbr, &p.d->m, &p.d->max_dplus, &p.d->dplus, tr);
-    p.rnbr.release(); p.bigq.release(); p.nbigq.release();
+    orient_rows_finish(g, p.d->rank.p, p.w, p.d->off, p.d->nbr, &p.d->m, &p.d->max_dplus, &p.d->dplus, tr);
+    GMSB_CUDA(cudaStreamSynchronize(rt().stream));
+    p.w = OrientRows();
+}
+
+// ---- sharded build: one vertex range per device --------------------------------------------------------------------------
+// After orient_rows_range over its range [u0, u1) a device packs its finished rows in original-id order (the "piece"),
+// the pieces and the d+ values are exchanged by the caller (one all-gather, one all-reduce), and every device moves all
+// rows into rank order.
+int64_t orient_piece_layout(const Graph &g, const vid_t *rank_dev, OrientRows &w, int64_t u0, int64_t u1,
+                            DevBuf<eid_t> &piece_off) {
+    Runtime &r = rt();
+    orient_rows_big(g, rank_dev, w);
+    orient_rows_sort(w);
+    piece_off.alloc((size_t)(u1 - u0) + 1);
+    if (u1 > u0) {
+        DevBuf<int> mx(1);
+        mx.zero();
+        k_max_i32<<<grid_for(u1 - u0, 256), 256, 0, r.stream>>>(w.dold.p + u0, u1 - u0, mx.p); launched();
+        GMSB_REQUIRE(mx.get(0) <= kSortCap, "sharded build: an oriented list is longer than the on-chip sorter holds");
+    }
+    exclusive_sum(w.dold.p + u0, piece_off.p, (u1 - u0) + 1);       // reads dold[u1]: the spare entry when u1 == n
+    return piece_off.get((size_t)(u1 - u0));
+}
+void orient_piece_export(const Graph &g, OrientRows &w, int64_t u0, int64_t u1, const DevBuf<eid_t> &piece_off,
+                         vid_t *piece_dst, int32_t *dplus_all) {
+    Runtime &r = rt();
+    if (u1 > u0) {
+        k_move_rows<false><<<grid_for(u1 - u0, 256), 256, 0, r.stream>>>(g.off.p, w.dold.p, w.trow.p, u0, u1, piece_off.p,
+                                                                        nullptr, piece_dst);
+        launched();
+        GMSB_CUDA(cudaMemcpyAsync(dplus_all + u0, w.dold.p + u0, sizeof(int32_t) * (size_t)(u1 - u0),
+                                  cudaMemcpyDeviceToDevice, r.stream));
+    }
+    GMSB_CUDA(cudaStreamSynchronize(r.stream));
+}
+void dag_from_pieces(Dag &d, const int32_t *dplus_all, const vid_t *pieces, int64_t stride, const int64_t *cut, int parts) {
+    Runtime &r = rt();
+    const int64_t n = d.n;
+    GMSB_REQUIRE(parts >= 1 && parts <= kMaxParts, "sharded build: too many parts");
+    offsets_by_rank(n, dplus_all, d.rank.p, d.off, &d.m, &d.max_dplus, &d.dplus);
+    d.nbr.alloc(d.m);
+    if (d.m == 0) return;
+    DevBuf<int32_t> len(n + 1);
+    len.zero();
+    GMSB_CUDA(cudaMemcpyAsync(len.p, dplus_all, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToDevice, r.stream));
+    DevBuf<eid_t> scan(n + 1), src_start(n);
+    exclusive_sum(len.p, scan.p, n + 1);
+    PartCuts pc{};
+    pc.parts = parts;
+    for (int i = 0; i <= parts; ++i) pc.cut[i] = cut[i];
+    k_piece_starts<<<grid_for(n, 256), 256, 0, r.stream>>>(scan.p, n, pc, stride, src_start.p); launched();
+    k_move_rows<true><<<grid_for(n, 256), 256, 0, r.stream>>>(src_start.p, len.p, pieces, 0, n, d.off.p, d.rank.p, d.nbr.p);
+    launched();
+    GMSB_CUDA(cudaStreamSynchronize(r.stream));
 }
 
 Dag *build_degree_dag(const Graph &g) {

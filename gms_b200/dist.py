@@ -70,6 +70,41 @@ def tc_total_sharded(graph, **opts):
     return total, part, stats
 
 
+class ShardedOrientedBuild:
+    """Host CSR -> oriented device graph with the work sharded over the ranks (gmsb_shard_*): rank r uploads and orients
+    the vertex range r of `world` (1/world of the neighbour array over its own host link), the finished rows are
+    all-gathered over NVLink and the d+ values all-reduced, and every rank moves the rows into rank order.  The graph
+    `build()` returns answers the triangle entry points (its symmetric lists are incomplete by construction).
+    Buffers are allocated once and reused by every `build()`."""
+
+    def __init__(self, offsets_host, nbrs_host, device, shard_factory=None):
+        self.rank, self.world = (dist.get_rank(), dist.get_world_size()) if dist.is_initialized() else (0, 1)
+        self.device = torch.device(device)
+        self.shard_factory = shard_factory          # tests drive the exchange on CPU tensors with a stand-in
+        self.off = offsets_host.numpy() if isinstance(offsets_host, torch.Tensor) else offsets_host
+        self.nbr = nbrs_host.numpy() if isinstance(nbrs_host, torch.Tensor) else nbrs_host
+        self.n = len(self.off) - 1
+        self.dplus = torch.zeros(max(self.n, 1), dtype=torch.int32, device=self.device)
+        self.pieces = None
+
+    def build(self):
+        if self.shard_factory is None:
+            from . import capi
+            self.shard_factory = capi.Shard
+        shard = self.shard_factory(self.off, self.nbr, self.rank, self.world)
+        stride = max(int(allreduce_max(shard.piece_len, device=self.device)), 1)
+        if self.pieces is None or self.pieces.numel() < stride * self.world:
+            self.pieces = torch.empty(stride * self.world, dtype=torch.int32, device=self.device)
+        pieces = self.pieces.narrow(0, 0, stride * self.world)
+        mine = pieces.narrow(0, self.rank * stride, stride)
+        self.dplus.zero_()
+        shard.export(mine.data_ptr(), self.dplus.data_ptr())
+        if self.world > 1:
+            dist.all_gather_into_tensor(pieces, mine)
+            dist.all_reduce(self.dplus, op=dist.ReduceOp.SUM)
+        return shard.finish(pieces.data_ptr(), stride, self.dplus.data_ptr())
+
+
 def _slice_len(total, world):
     return (total + world - 1) // world
 

@@ -92,6 +92,26 @@ GMSB_API int gmsb_graph_from_csr_device(int64_t n, const int64_t *offsets, const
 typedef enum { GMSB_BUILD_DEFAULT = 0, GMSB_BUILD_ORIENT = 1 } gmsb_build_flags;
 GMSB_API int gmsb_graph_from_csr_ex(int64_t n, const int64_t *offsets, const int32_t *nbrs, int directed, int flags,
                                     gmsb_graph_t *out);
+/* Sharded form of the same construction for one process per device (torchrun ranks, MPI ranks): SURVEY.md 8e keeps the
+ * CSR replicated, but what the triangle kernels read is the ORIENTED representation only, so each device uploads and
+ * orients one vertex range and the finished rows are exchanged instead of the host arrays being read N times.
+ *   gmsb_shard_begin   device part_index of part_count uploads the offsets and the neighbour slots of its vertex range
+ *                      (ranges of equal slot counts), ranks the vertices (PpParallel::getDegreeOrdering), keeps each
+ *                      row's higher-ranked neighbours, relabelled and sorted; *piece_len = entries of its piece
+ *   gmsb_shard_export  writes the piece (rows packed in original-id order) to piece_dev and d+ of the range's vertices
+ *                      to dplus_all_dev[range] (an int32[n] the caller zeroed)
+ *   (caller)           all-gather of the pieces into pieces_dev[part * piece_stride ...], piece_stride >= every
+ *                      piece_len; all-reduce(sum) of dplus_all_dev
+ *   gmsb_shard_finish  rows into rank order; the handle it returns answers gmsb_tc_total[_ex] / gmsb_tc_vertex2 and the
+ *                      size queries — its symmetric lists are incomplete, every other operator returns GMSB_ERR_INVALID
+ * Lists longer than 8192 after orientation are not supported here (GMSB_ERR_INVALID): use gmsb_graph_from_csr_ex. */
+typedef struct gmsb_shard_s *gmsb_shard_t;
+GMSB_API int gmsb_shard_begin(int64_t n, const int64_t *offsets, const int32_t *nbrs, int part_index, int part_count,
+                              gmsb_shard_t *out, int64_t *piece_len);
+GMSB_API int gmsb_shard_export(gmsb_shard_t s, int32_t *piece_dev, int32_t *dplus_all_dev);
+GMSB_API int gmsb_shard_finish(gmsb_shard_t s, const int32_t *pieces_dev, int64_t piece_stride, const int32_t *dplus_all_dev,
+                               gmsb_graph_t *out);
+GMSB_API int gmsb_shard_free(gmsb_shard_t s);
 /* BuilderBase::MakeGraphFromEL + SquishGraph            gms/third_party/gapbs/builder.h:279-298,237-251
  * n = max id + 1; symmetrize inserts both directions; lists sorted, de-duplicated, self loops removed —
  * done by an on-GPU radix sort of 64-bit (u<<32|v) keys. */

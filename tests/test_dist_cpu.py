@@ -6,6 +6,7 @@ import socket
 import sys
 
 import numpy as np
+import pytest
 import torch.multiprocessing as mp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -88,6 +89,101 @@ def test_sharded_csr_upload_replicates_the_host_arrays():
     for p in procs:
         p.start()
     res = sorted(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res)
+
+
+# ---- the exchange of the sharded build (gms_b200.dist.ShardedOrientedBuild) over gloo ----------------------------------
+class NumpyShard:
+    """CPU stand-in with the interface of gms_b200.capi.Shard that restates the gmsb_shard_* protocol in numpy
+    (gms_b200/csrc/graph_build.cu: shard_begin / shard_export / shard_finish): vertex cuts of equal slot counts, rows of
+    the own range oriented by (degree, id) rank and packed in original-id order, rows of all pieces moved into rank order
+    with  start(u) = scan[u] - scan[cut[r]] + r * stride."""
+
+    def __init__(self, off, nbr, part, parts):
+        self.off, self.nbr, self.part, self.parts = off, nbr, part, parts
+        n = self.n = len(off) - 1
+        last = int(off[n])
+        self.cut = [0]
+        for i in range(1, parts):
+            self.cut.append(max(self.cut[-1], int(np.searchsorted(off[:n], last // parts * i, "left"))))
+        self.cut.append(n)
+        deg = np.diff(off)
+        order = np.lexsort((np.arange(n), deg))                    # (degree asc, id asc)
+        self.rank = np.empty(n, np.int64)
+        self.rank[order] = np.arange(n)
+        u0, u1 = self.cut[part], self.cut[part + 1]
+        self.rows = []
+        for u in range(u0, u1):
+            r = self.rank[nbr[off[u]:off[u + 1]]]
+            self.rows.append(np.sort(r[r > self.rank[u]]).astype(np.int32))
+        self.piece_len = int(sum(len(r) for r in self.rows))
+
+    @staticmethod
+    def _view(ptr, count):
+        import ctypes
+        return np.ctypeslib.as_array((ctypes.c_int32 * max(count, 1)).from_address(ptr))[:count]
+
+    def export(self, piece_ptr, dplus_all_ptr):
+        piece = self._view(piece_ptr, self.piece_len)
+        if self.rows:
+            piece[:] = np.concatenate(self.rows) if self.piece_len else piece
+        dplus = self._view(dplus_all_ptr, self.n)
+        u0 = self.cut[self.part]
+        dplus[u0:u0 + len(self.rows)] = [len(r) for r in self.rows]
+
+    def finish(self, pieces_ptr, stride, dplus_all_ptr):
+        n = self.n
+        dplus = self._view(dplus_all_ptr, n).astype(np.int64)
+        pieces = self._view(pieces_ptr, stride * self.parts)
+        scan = np.concatenate([[0], np.cumsum(dplus)])
+        doff = np.zeros(n + 1, np.int64)
+        doff[self.rank + 1] = dplus
+        doff = np.cumsum(doff)
+        dnbr = np.empty(int(doff[n]), np.int32)
+        for r in range(self.parts):
+            for u in range(self.cut[r], self.cut[r + 1]):
+                start = int(scan[u] - scan[self.cut[r]] + r * stride)
+                dnbr[doff[self.rank[u]]:doff[self.rank[u]] + dplus[u]] = pieces[start:start + dplus[u]]
+        return doff, dnbr
+
+
+def _sharded_build_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    import torch
+    from gms_b200 import dist as gd
+    from oracle import binding
+    gd.init(backend="gloo")
+    orc = binding.oracle()
+    ok = True
+    for scale in (6, 9):
+        g = orc.generate(scale)
+        off, nbr = g.csr()
+        want_off, want_nbr = g.induce_directed(g.degree_order(True)).csr()
+        build = gd.ShardedOrientedBuild(torch.from_numpy(off.astype(np.int64)), torch.from_numpy(nbr.astype(np.int32)),
+                                        "cpu", shard_factory=NumpyShard)
+        for _ in range(2):                                           # buffers are reused
+            doff, dnbr = build.build()
+            m = int(doff[-1])
+            ok &= bool(np.array_equal(doff[:len(want_off)], want_off) and np.array_equal(dnbr[:m], want_nbr[:m]))
+            ok &= bool(np.all(doff[len(want_off) - 1:] == m))        # vertices past the last endpoint have empty rows
+    gd.barrier()
+    q.put((rank, ok))
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_oriented_build_exchange(world):
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sharded_build_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=240) for _ in range(world))
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
