@@ -3,7 +3,7 @@
 //
 // oracle.cpp: an independent CPU restatement of the reference's (spcl/gms) algorithms for the
 // set-intersection hot path, written from the behaviour described at the cited reference lines
-// (paths relative to /root/reference).  PARITY IS PINNED: tests/test_oracle_vs_reference.py checks every
+// (paths relative to /root/reference).  PARITY IS PINNED: tests/test_oracle_golden.py checks every
 // function below against the unmodified reference (oracle/_ref/libgmsref.so, built from the reference's own
 // sources by oracle/Makefile) when that library is present, and tests/golden/*.json holds vectors generated
 // from the reference itself (tests/golden/make_golden.py) plus the reference's own KATs
