@@ -410,9 +410,9 @@ def run_ours(args):
     bm_ms = float(np.mean(ms_bitmap))
     count_ms = float(np.mean(ms_count))
     sched_ms = float(np.mean(ms_sched))
-    alg_bytes = st["bytes_bitmap"] / max(world, 1)
-    # (wedges_bitmap is a whole-graph figure; edges_bitmap / bitmap_items are this rank's share of the schedule)
-    min_traffic = 4.0 * st["wedges_bitmap"] / max(world, 1) + 8.0 * st["edges_bitmap"] + 32.0 * st["bitmap_items"]
+    # (N > 1: every statistic of the schedule is this rank's share, like the kernel time beside it)
+    alg_bytes = st["bytes_bitmap"]
+    min_traffic = 4.0 * st["wedges_bitmap"] + 8.0 * st["edges_bitmap"] + 32.0 * st["bitmap_items"]
     cap = ncu_capture("k_tc_bitmap2") if world == 1 else None
     achieved = min_traffic / (bm_ms * 1e-3) / 1e9 if bm_ms > 0 else 0.0
     roofline = {

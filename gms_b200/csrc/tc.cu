@@ -41,9 +41,11 @@ namespace {
 //           k_plan_layout   per vertex: the counters become absolute write cursors (or a LIGHT / DEAD mark), items written
 //   pass 2  k_plan_scatter  one ATOM per edge into an owned hub takes the descriptor's slot in v's segment; edges into
 //                           light vertices are appended to the merge / gallop lists instead (warp-aggregated cursors)
-// With part_count > 1 a device builds ITS SHARE of the schedule only: pass 1 and the classification are global (the
-// deal of the hubs needs every hub's work), everything after them — segments, items, cursors, descriptor writes, item
-// order — covers the hubs dealt to this device and the light edges whose slot number names it.
+// With part_count > 1 a device builds ITS SHARE of the schedule only.  An edge (u,v) belongs to the device that owns its
+// closing vertex v, and ownership is a function of the id alone — plan_owner: the vertices are dealt in snake order from
+// the top of rank space, where the hubs are, heaviest first — so every pass skips foreign edges right after loading v:
+// no gather, no atomic, no write.  Counters, classification, segments, items, descriptor writes and the item order cover
+// the own vertices only, and every statistic of the schedule is this device's share (the shares add up).
 // Round 1 emitted 251 M (key, descriptor) pairs at scale 24 and radix-sorted them (4 onesweep passes over 12 B per
 // pair + 2 x 251 M 64-bit atomics for the per-vertex work) and then flagged / scanned / compacted the light edges.
 constexpr int kCntShift = 38;                                  // counter word = (descriptors << 38) | sum of lengths
@@ -55,15 +57,19 @@ constexpr unsigned long long kPosDead = 1ull << 62;            // ... and into a
 constexpr uint8_t kDead = 0;        // no incoming descriptor can close a triangle
 constexpr uint8_t kLight = 1;       // edges go to the merge / gallop lists
 constexpr uint8_t kHub = 2;         // hub whose descriptor segment this device builds
-constexpr uint8_t kHubElsewhere = 3;        // hub dealt to another device (part_count > 1)
+constexpr uint8_t kElsewhere = 3;   // vertex owned by another device (part_count > 1)
+
+// owner of closing vertex v among P devices: rank space puts the highest degrees last, so counting from the top deals
+// the hubs out in (nearly) descending order of work; the snake order evens out the steps between neighbours
+__device__ __forceinline__ int plan_owner(vid_t v, int64_t n, int P) { return snake_owner((int)(n - 1 - (int64_t)v), P); }
 
 __device__ __forceinline__ uint32_t len_class(eid_t len) { return len <= kShortLen ? 0u : (len <= kMidLen ? 1u : 2u); }
 
 template <int G>
 __global__ void __launch_bounds__(256)
 k_plan_count(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, const int32_t *__restrict__ dplus,
-             int64_t n, unsigned long long *__restrict__ cw /* 3n */,
-             unsigned long long *__restrict__ acc /* [0]=sum d+(u)+d+(v), all edges  [1]=wedges  [2]=kept edges
+             int64_t n, int part_index, int part_count, unsigned long long *__restrict__ cw /* 3n */,
+             unsigned long long *__restrict__ acc /* over the own edges: [0]=sum d+(u)+d+(v)  [1]=wedges  [2]=kept edges
                                                      [3]=sum d+(u), kept edges */) {
     const int sub = threadIdx.x % G;
     const int64_t grp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / G;
@@ -74,6 +80,7 @@ k_plan_count(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, const
         const unsigned long long du = (unsigned long long)(e - b);
         for (eid_t s = b + sub; s < e; s += G) {
             const vid_t v = nbr[s];
+            if (part_count > 1 && plan_owner(v, n, part_count) != part_index) continue;
             const int dv = dplus[v];
             const eid_t len = e - s - 1;
             deg2 += du + (unsigned long long)dv;
@@ -103,17 +110,19 @@ struct PlanParams {
 
 // Per vertex: hub or not, and into how many CTA items its descriptor group is cut.
 __global__ void k_classify(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, int64_t n,
-                           const unsigned long long *__restrict__ cw, PlanParams pp,
+                           const unsigned long long *__restrict__ cw, PlanParams pp, int part_index, int part_count,
                            int64_t *__restrict__ nitems /* n+1 */, int64_t *__restrict__ seg /* n+1 */,
                            unsigned long long *__restrict__ cls /* [0]=hub edges [1]=hub wedges [2]=sum cnt*d+(v), hubs
                                                                   [3]=sum cnt*d+(v), all  [4]=light edges */,
                            int *__restrict__ mx /* [0]=max span words [1]=max d+ of a hub */,
-                           uint8_t *__restrict__ vstate /* n: kDead / kLight / kHub */) {
+                           uint8_t *__restrict__ vstate /* n: kDead / kLight / kHub / kElsewhere */) {
     int mxw = 0, mxd = 0;
     unsigned long long he = 0, hw = 0, hb = 0, ab = 0, le = 0;
     for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v <= n; v += (int64_t)gridDim.x * blockDim.x) {
         int64_t k = 0, sg = 0;
-        if (v < n) {
+        if (v < n && part_count > 1 && plan_owner((vid_t)v, n, part_count) != part_index) {
+            vstate[v] = kElsewhere;
+        } else if (v < n) {
             const unsigned long long w0 = cw[3 * v], w1 = cw[3 * v + 1], w2 = cw[3 * v + 2];
             const int64_t cnt = (int64_t)((w0 >> kCntShift) + (w1 >> kCntShift) + (w2 >> kCntShift));
             uint8_t state = kDead;
@@ -167,16 +176,14 @@ __global__ void k_classify(const eid_t *__restrict__ off, const vid_t *__restric
 // Counters -> write cursors; items of the hubs (a slice of the descriptor segment each, with its class boundaries).
 __global__ void k_plan_layout(int64_t n, unsigned long long *__restrict__ cw, const int64_t *__restrict__ nitems,
                               const int64_t *__restrict__ item_base, const int64_t *__restrict__ segbase,
-                              const int32_t *__restrict__ deal, const uint8_t *__restrict__ vstate,
-                              Item *__restrict__ items) {
+                              const uint8_t *__restrict__ vstate, Item *__restrict__ items) {
     for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x) {
         const int64_t c0 = (int64_t)(cw[3 * v] >> kCntShift), c1 = (int64_t)(cw[3 * v + 1] >> kCntShift),
                       c2 = (int64_t)(cw[3 * v + 2] >> kCntShift);
         const int64_t cnt = c0 + c1 + c2, k = nitems[v];
         const uint8_t state = vstate[v];
-        if (state == kDead || state == kHubElsewhere) {
-            cw[3 * v] = kPosDead; cw[3 * v + 1] = kPosDead; cw[3 * v + 2] = kPosDead; continue;
-        }
+        if (state == kElsewhere) continue;                      // another device's vertex: its counters were never touched
+        if (state == kDead) { cw[3 * v] = kPosDead; cw[3 * v + 1] = kPosDead; cw[3 * v + 2] = kPosDead; continue; }
         if (state == kLight) { cw[3 * v] = kPosLight; cw[3 * v + 1] = kPosLight; cw[3 * v + 2] = kPosLight; continue; }
         const int64_t b = segbase[v];
         cw[3 * v] = (unsigned long long)b;
@@ -187,7 +194,7 @@ __global__ void k_plan_layout(int64_t n, unsigned long long *__restrict__ cw, co
             const int64_t s = j * chunk;                           // first descriptor of the slice, relative to b
             const int64_t c = cnt - s < chunk ? cnt - s : chunk;
             Item it;
-            it.v = (int32_t)v; it.begin = b + s; it.count = (int32_t)c; it.deal = deal[v]; it.pad = 0;
+            it.v = (int32_t)v; it.begin = b + s; it.count = (int32_t)c; it.pad[0] = 0; it.pad[1] = 0;
             const int64_t a0 = c0 - s, a1 = c0 + c1 - s;
             it.n0 = (int32_t)(a0 < 0 ? 0 : (a0 > c ? c : a0));
             it.n1 = (int32_t)(a1 < 0 ? 0 : (a1 > c ? c : a1));
@@ -203,7 +210,7 @@ k_plan_scatter(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, con
                uint64_t *__restrict__ desc, int variant, int ratio, int part_index, int part_count,
                uint64_t *__restrict__ m_desc, vid_t *__restrict__ m_v, uint64_t *__restrict__ g_desc,
                vid_t *__restrict__ g_v, unsigned long long *__restrict__ cursors /* [0]=merge [1]=gallop */,
-               unsigned long long *__restrict__ acc /* [0] = sum of d+(u) over hub edges (every device's) */) {
+               unsigned long long *__restrict__ acc /* [0] = sum of d+(u) over the own hub edges */) {
     namespace cg = cooperative_groups;
     const int sub = threadIdx.x % G;
     const int64_t grp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / G;
@@ -215,16 +222,15 @@ k_plan_scatter(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, con
             const eid_t len = e - s - 1;
             if (len <= 0) continue;
             const vid_t v = nbr[s];
+            if (part_count > 1 && plan_owner(v, n, part_count) != part_index) continue;
             const uint8_t state = vstate[v];
             if (state == kDead) continue;
             const uint64_t ds = ((uint64_t)(s + 1) << kLenBits) | (uint64_t)len;
-            if (state >= kHub) {
+            if (state == kHub) {
                 hub_u += (unsigned long long)(e - b);
-                if (state == kHub) desc[atomicAdd(&pos[3 * (int64_t)v + len_class(len)], 1ull)] = ds;
+                desc[atomicAdd(&pos[3 * (int64_t)v + len_class(len)], 1ull)] = ds;
                 continue;
             }
-            // light edge: it belongs to the device its slot number names (the same rule the counting kernels apply)
-            if (part_count > 1 && (int)((uint64_t)(s + 1) % (uint64_t)part_count) != part_index) continue;
             const long long a = (long long)len, dv = dplus[v];
             const long long lo = a < dv ? a : dv, hi = a < dv ? dv : a;
             const bool gallop = variant == GMSB_TC_GALLOP || (variant != GMSB_TC_MERGE && hi >= (long long)ratio * lo);
@@ -271,33 +277,6 @@ __global__ void k_item_keys(const Item *__restrict__ items, int64_t cnt, int64_t
         atomicAdd(&cls_count[cls], 1ull);
         atomicMax(&cls_words[cls], words);
         keys[i] = ((uint64_t)cls << 62) | ((tile & 0x3fffffffull) << 32) | (uint64_t)(uint32_t)(n - 1 - it.v);
-    }
-}
-
-// Multi-device partition.  Hubs are dealt to the devices as whole vertices — the descriptors inside v's segment sit in
-// the order the scatter pass's atomics happened to run in, so a slice of it is not the same set of edges on two
-// devices — in snake order over the hubs sorted by descending work (deterministic; the heaviest hubs alternate).
-__global__ void k_hub_keys(int64_t n, const int64_t *__restrict__ nitems, const unsigned long long *__restrict__ cw,
-                           uint64_t *__restrict__ keys, int *__restrict__ nhubs) {
-    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x) {
-        if (nitems[v] == 0) continue;
-        const unsigned long long work = (cw[3 * v] & kWorkMask) + (cw[3 * v + 1] & kWorkMask) + (cw[3 * v + 2] & kWorkMask);
-        keys[atomicAdd(nhubs, 1)] = ((kWorkMask - (work & kWorkMask)) << 26) | (unsigned long long)v;     // heaviest first
-    }
-}
-__global__ void k_hub_deal(const uint64_t *__restrict__ sorted, int nhubs, int32_t *__restrict__ deal) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nhubs; i += gridDim.x * blockDim.x)
-        deal[sorted[i] & ((1ull << 26) - 1ull)] = i;
-}
-// part_count > 1: a device lays out, fills and orders only the segments of the hubs it owns; the others lose their
-// items and their segment before the scans, so nothing downstream sees them.
-__global__ void k_plan_own(int64_t n, const int32_t *__restrict__ deal, int part_index, int part_count,
-                           int64_t *__restrict__ nitems, int64_t *__restrict__ seg, uint8_t *__restrict__ vstate) {
-    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x) {
-        if (vstate[v] != kHub || snake_owner(deal[v], part_count) == part_index) continue;
-        vstate[v] = kHubElsewhere;
-        nitems[v] = 0;
-        seg[v] = 0;
     }
 }
 
@@ -671,15 +650,15 @@ TcPlan *build_plan(const Dag &d, const gmsb_tc_options &opt) {
         DevBuf<unsigned long long> cw(3 * (size_t)n), acc(4), cls(5);
         DevBuf<int> mx(2);
         cw.zero(); acc.zero(); cls.zero(); mx.zero();
-        k_plan_count<G><<<grid_for(n * G, 256), 256, 0, r.stream>>>(d.off.p, d.nbr.p, d.dplus.p, n, cw.p, acc.p);
+        k_plan_count<G><<<grid_for(n * G, 256), 256, 0, r.stream>>>(d.off.p, d.nbr.p, d.dplus.p, n, pi, P, cw.p, acc.p);
         launched();
         tr.mark("plan: count pass");
         DevBuf<int64_t> nitems(n + 1), seg(n + 1), item_base(n + 1), segbase(n + 1);
         DevBuf<uint8_t> vstate(n);
         PlanParams pp{opt.variant, hub_bits, (long long)opt.hub_min_work,
                       opt.reserved[0] > 0 ? (long long)opt.reserved[0] : 262144ll};
-        k_classify<<<grid_for(n + 1, 256), 256, 0, r.stream>>>(d.off.p, d.nbr.p, n, cw.p, pp, nitems.p, seg.p, cls.p,
-                                                              mx.p, vstate.p);
+        k_classify<<<grid_for(n + 1, 256), 256, 0, r.stream>>>(d.off.p, d.nbr.p, n, cw.p, pp, pi, P, nitems.p, seg.p,
+                                                              cls.p, mx.p, vstate.p);
         launched();
         unsigned long long h_acc[4], h_cls[5];
         int h_mx[2];
@@ -695,25 +674,6 @@ TcPlan *build_plan(const Dag &d, const gmsb_tc_options &opt) {
         p->max_hub_dplus = h_mx[1];
         const int64_t n_light = (int64_t)h_cls[4];
         if (p->n_desc == 0) return p;
-        // whole hubs are dealt to the devices (deal = position by descending work); with several devices the ones
-        // dealt elsewhere drop out here, before the scans lay out items and segments
-        GMSB_REQUIRE(n <= (int64_t(1) << 26), "tc: too many vertices for the hub deal key");
-        DevBuf<int32_t> deal(n);
-        {
-            DevBuf<uint64_t> hk(n), hk2(n);
-            DevBuf<int> nh(1);
-            nh.zero();
-            k_hub_keys<<<grid_for(n, 256), 256, 0, r.stream>>>(n, nitems.p, cw.p, hk.p, nh.p); launched();
-            const int n_hubs = nh.get(0);
-            if (n_hubs) {
-                uint64_t *sorted = radix_sort_keys(hk.p, hk2.p, n_hubs, 0, 64);
-                k_hub_deal<<<grid_for(n_hubs, 256), 256, 0, r.stream>>>(sorted, n_hubs, deal.p); launched();
-                if (P > 1) {
-                    k_plan_own<<<grid_for(n, 256), 256, 0, r.stream>>>(n, deal.p, pi, P, nitems.p, seg.p, vstate.p);
-                    launched();
-                }
-            }
-        }
         exclusive_sum(nitems.p, item_base.p, n + 1);
         exclusive_sum(seg.p, segbase.p, n + 1);
         tr.mark("plan: classify + scans");
@@ -721,11 +681,10 @@ TcPlan *build_plan(const Dag &d, const gmsb_tc_options &opt) {
         p->n_bitmap_edges = segbase.get(n);
         p->items.alloc(p->n_items);
         p->desc.alloc(p->n_bitmap_edges);
-        k_plan_layout<<<grid_for(n, 256), 256, 0, r.stream>>>(n, cw.p, nitems.p, item_base.p, segbase.p, deal.p, vstate.p,
+        k_plan_layout<<<grid_for(n, 256), 256, 0, r.stream>>>(n, cw.p, nitems.p, item_base.p, segbase.p, vstate.p,
                                                              p->items.p);
         launched();
-        // both light lists are sized for all light edges (an upper bound for this device's share: light edges are dealt
-        // by slot number); the scatter pass decides merge / gallop per edge
+        // both light lists are sized for all of this device's light edges; the scatter pass decides merge / gallop per edge
         p->m_desc.alloc(n_light); p->m_v.alloc(n_light); p->g_desc.alloc(n_light); p->g_v.alloc(n_light);
         DevBuf<unsigned long long> cursors(2), hub_u(1);
         cursors.zero(); hub_u.zero();
@@ -808,9 +767,8 @@ void tc_total(Graph &g, const gmsb_tc_options &opt_in, uint64_t *out, gmsb_tc_st
 
     DevBuf<unsigned long long> total(1);
     total.zero();
-    const int P = opt.part_count, pi = opt.part_index;
-    // the schedule holds this device's share only (whole hubs by deal position, light edges by slot number: ownership
-    // does not depend on the order the scatter pass's atomics ran in)
+    // the schedule holds this device's share only (the edges into the vertices it owns: ownership does not depend on
+    // the order the scatter pass's atomics ran in)
     const int64_t my_items = p.n_items, my_merge = p.n_merge, my_gallop = p.n_gallop;
 
     t_bm.start();
@@ -882,8 +840,8 @@ void tc_total(Graph &g, const gmsb_tc_options &opt_in, uint64_t *out, gmsb_tc_st
     if (stats) {
         gmsb_tc_stats s{};
         s.triangles = *out;
-        s.algorithmic_bytes = p.algorithmic_bytes / P + (pi == 0 ? p.algorithmic_bytes % P : 0);
-        s.wedges_checked = p.wedges / P;
+        s.algorithmic_bytes = p.algorithmic_bytes;            // every figure of the schedule is this device's share
+        s.wedges_checked = p.wedges;
         s.oriented_edges = d.m;
         s.edges_bitmap = p.n_bitmap_edges;                    // this device's share, like bitmap_items
         s.edges_merge = p.n_merge;

@@ -23,11 +23,10 @@ struct Item {            // one CTA work unit: a slice of hub v's incoming descr
     int32_t count;       // descriptors in the slice
     int32_t n0, n1;      // [0,n0) class 0, [n0,n1) class 1, [n1,count) class 2
     int64_t begin;
-    int32_t deal;        // position of v among the hubs by descending work: multi-device owner = snake(deal, devices)
-    int32_t pad;
+    int32_t pad[2];
 };
 
-// owner of deal position d among P devices: 0 1 .. P-1 P-1 .. 1 0 0 1 ..
+// owner of position d of a deal among P devices: 0 1 .. P-1 P-1 .. 1 0 0 1 ..
 __host__ __device__ inline int snake_owner(int d, int P) {
     const int r = d % (2 * P);
     return r < P ? r : 2 * P - 1 - r;
@@ -46,7 +45,8 @@ struct TcPlan {
     DevBuf<uint64_t> m_desc, g_desc;    // light edges for merge / gallop
     DevBuf<vid_t> m_v, g_v;
     int64_t n_merge = 0, n_gallop = 0, n_bitmap_edges = 0;
-    uint64_t algorithmic_bytes = 0;     // B_TC over ALL oriented edges
+    // (with part_count > 1 every figure below covers this device's share of the edges: those into the vertices it owns)
+    uint64_t algorithmic_bytes = 0;     // B_TC over the oriented edges
     uint64_t wedges = 0;
     uint64_t bytes_bitmap = 0, bytes_kept = 0, wedges_bitmap = 0;
     int max_hub_dplus = 0;              // largest d+ among hub vertices (tc_support sizes its shared lists with it)

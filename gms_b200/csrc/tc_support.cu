@@ -202,7 +202,7 @@ __global__ void k_edge_scores(const eid_t *__restrict__ off, const vid_t *__rest
 }  // namespace
 
 // support of every oriented edge, in the DAG's CSR order (rank space).  part_index / part_count: this device credits
-// the triangles of its share of the schedule only (items and light edges dealt round-robin as in tc_total); the shares
+// the triangles of its share of the schedule only (the edges into the vertices it owns, as in tc_total); the shares
 // add up to the full support (multi-GPU: one all-reduce, mgpu.cu).
 void tc_support(Graph &g, DevBuf<uint32_t> &sup, int pi, int P) {
     Runtime &r = rt();

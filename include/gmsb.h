@@ -166,8 +166,9 @@ typedef enum { GMSB_TC_AUTO = 0, GMSB_TC_MERGE = 1, GMSB_TC_GALLOP = 2, GMSB_TC_
 
 typedef struct {
     int32_t variant;         /* gmsb_tc_variant */
-    int32_t part_index;      /* this process handles share part_index of part_count of the oriented edges   */
-    int32_t part_count;      /* (multi-GPU: edge partition balanced by work, CSR replicated); 0 or 1 = all    */
+    int32_t part_index;      /* this process handles share part_index of part_count of the oriented edges:  */
+    int32_t part_count;      /* those whose closing vertex it owns (vertices dealt from the top of the degree
+                                order; the schedule is built for the share only); 0 or 1 = all                */
     int32_t reuse_plan;      /* 0: build the oriented DAG and the schedule for this call and drop them; 1: keep
                                 both cached on the handle between calls; 2: keep the DAG (the FromCGraph analogue),
                                 rebuild the kernel-specific schedule on every call                             */
@@ -180,7 +181,7 @@ typedef struct {
 typedef struct {
     uint64_t triangles;        /* this part's count (sum over parts = total)                                   */
     uint64_t algorithmic_bytes;/* B_TC share: sum over this part's oriented edges of 4*(d+(u)+d+(v))            */
-    uint64_t wedges_checked;   /* list elements actually probed                                                */
+    uint64_t wedges_checked;   /* list elements actually probed (this part)                                    */
     int64_t oriented_edges;    /* |E+| of the whole graph                                                       */
     int64_t edges_bitmap, edges_merge, edges_gallop;   /* this part's edges by kernel                          */
     double ms_orient;          /* device ms: degree ranking + DAG build + schedule                              */
@@ -188,10 +189,10 @@ typedef struct {
     double ms_bitmap, ms_merge, ms_gallop;             /* per-kernel device ms (launched back to back)          */
     int32_t launches;          /* kernels launched by this call                                                 */
     int32_t max_dplus;
-    uint64_t bytes_bitmap;     /* algorithmic bytes of the edges the bitmap kernel handles (whole graph)        */
+    uint64_t bytes_bitmap;     /* algorithmic bytes of the edges the bitmap kernel handles (this part)          */
     uint64_t bytes_light;      /* ... of the edges the merge + gallop kernels handle                            */
-    uint64_t wedges_bitmap;    /* list elements the bitmap kernel probes (whole graph)                          */
-    int64_t bitmap_items;      /* CTAs of the bitmap kernel (whole graph)                                       */
+    uint64_t wedges_bitmap;    /* list elements the bitmap kernel probes (this part)                            */
+    int64_t bitmap_items;      /* work items of the bitmap kernel (this part)                                   */
     int32_t bitmap_smem_bytes; /* dynamic shared memory per CTA of the bitmap kernel                            */
     int32_t reserved;
 } gmsb_tc_stats;
