@@ -59,16 +59,18 @@ constexpr uint8_t kLight = 1;       // edges go to the merge / gallop lists
 constexpr uint8_t kHub = 2;         // hub whose descriptor segment this device builds
 constexpr uint8_t kElsewhere = 3;   // vertex owned by another device (part_count > 1)
 
-// owner of closing vertex v among P devices: rank space puts the highest degrees last, so counting from the top deals
-// the hubs out in (nearly) descending order of work; the snake order evens out the steps between neighbours
-__device__ __forceinline__ int plan_owner(vid_t v, int64_t n, int P) { return snake_owner((int)(n - 1 - (int64_t)v), P); }
+// owner of closing vertex v among the devices: rank space puts the highest degrees last, so counting from the top deals
+// the hubs out in (nearly) descending order of work; the snake order evens out the steps between neighbours (owner.cuh)
+__device__ __forceinline__ int plan_owner(vid_t v, int64_t n, const OwnerDeal &od) {
+    return deal_owner(od, (uint32_t)(n - 1 - (int64_t)v));
+}
 
 __device__ __forceinline__ uint32_t len_class(eid_t len) { return len <= kShortLen ? 0u : (len <= kMidLen ? 1u : 2u); }
 
 template <int G>
 __global__ void __launch_bounds__(256)
 k_plan_count(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, const int32_t *__restrict__ dplus,
-             int64_t n, int part_index, int part_count, unsigned long long *__restrict__ cw /* 3n */,
+             int64_t n, int part_index, OwnerDeal od, unsigned long long *__restrict__ cw /* 3n */,
              unsigned long long *__restrict__ acc /* over the own edges: [0]=sum d+(u)+d+(v)  [1]=wedges  [2]=kept edges
                                                      [3]=sum d+(u), kept edges */) {
     const int sub = threadIdx.x % G;
@@ -80,7 +82,7 @@ k_plan_count(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, const
         const unsigned long long du = (unsigned long long)(e - b);
         for (eid_t s = b + sub; s < e; s += G) {
             const vid_t v = nbr[s];
-            if (part_count > 1 && plan_owner(v, n, part_count) != part_index) continue;
+            if (od.parts > 1 && plan_owner(v, n, od) != part_index) continue;
             const int dv = dplus[v];
             const eid_t len = e - s - 1;
             deg2 += du + (unsigned long long)dv;
@@ -110,7 +112,7 @@ struct PlanParams {
 
 // Per vertex: hub or not, and into how many CTA items its descriptor group is cut.
 __global__ void k_classify(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, int64_t n,
-                           const unsigned long long *__restrict__ cw, PlanParams pp, int part_index, int part_count,
+                           const unsigned long long *__restrict__ cw, PlanParams pp, int part_index, OwnerDeal od,
                            int64_t *__restrict__ nitems /* n+1 */, int64_t *__restrict__ seg /* n+1 */,
                            unsigned long long *__restrict__ cls /* [0]=hub edges [1]=hub wedges [2]=sum cnt*d+(v), hubs
                                                                   [3]=sum cnt*d+(v), all  [4]=light edges */,
@@ -120,7 +122,7 @@ __global__ void k_classify(const eid_t *__restrict__ off, const vid_t *__restric
     unsigned long long he = 0, hw = 0, hb = 0, ab = 0, le = 0;
     for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v <= n; v += (int64_t)gridDim.x * blockDim.x) {
         int64_t k = 0, sg = 0;
-        if (v < n && part_count > 1 && plan_owner((vid_t)v, n, part_count) != part_index) {
+        if (v < n && od.parts > 1 && plan_owner((vid_t)v, n, od) != part_index) {
             vstate[v] = kElsewhere;
         } else if (v < n) {
             const unsigned long long w0 = cw[3 * v], w1 = cw[3 * v + 1], w2 = cw[3 * v + 2];
@@ -207,7 +209,7 @@ template <int G>
 __global__ void __launch_bounds__(256)
 k_plan_scatter(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, const int32_t *__restrict__ dplus,
                const uint8_t *__restrict__ vstate, int64_t n, unsigned long long *__restrict__ pos /* 3n */,
-               uint64_t *__restrict__ desc, int variant, int ratio, int part_index, int part_count,
+               uint64_t *__restrict__ desc, int variant, int ratio, int part_index, OwnerDeal od,
                uint64_t *__restrict__ m_desc, vid_t *__restrict__ m_v, uint64_t *__restrict__ g_desc,
                vid_t *__restrict__ g_v, unsigned long long *__restrict__ cursors /* [0]=merge [1]=gallop */,
                unsigned long long *__restrict__ acc /* [0] = sum of d+(u) over the own hub edges */) {
@@ -222,7 +224,7 @@ k_plan_scatter(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, con
             const eid_t len = e - s - 1;
             if (len <= 0) continue;
             const vid_t v = nbr[s];
-            if (part_count > 1 && plan_owner(v, n, part_count) != part_index) continue;
+            if (od.parts > 1 && plan_owner(v, n, od) != part_index) continue;
             const uint8_t state = vstate[v];
             if (state == kDead) continue;
             const uint64_t ds = ((uint64_t)(s + 1) << kLenBits) | (uint64_t)len;
@@ -633,7 +635,8 @@ TcPlan *build_plan(const Dag &d, const gmsb_tc_options &opt) {
     try {
         p->opt = opt;
         const int64_t n = d.n, m = d.m;
-        const int P = opt.part_count, pi = opt.part_index;
+        const int pi = opt.part_index;
+        const OwnerDeal od = make_owner_deal(opt.part_count);
         GMSB_REQUIRE(d.max_dplus < (1 << kLenBits), "tc: out-degree too large for the descriptor format");
         GMSB_REQUIRE(m < (int64_t(1) << (64 - kLenBits)), "tc: too many edges for the descriptor format");
         // the per-(vertex, class) counter packs (descriptors << 38 | sum of suffix lengths)
@@ -650,14 +653,14 @@ TcPlan *build_plan(const Dag &d, const gmsb_tc_options &opt) {
         DevBuf<unsigned long long> cw(3 * (size_t)n), acc(4), cls(5);
         DevBuf<int> mx(2);
         cw.zero(); acc.zero(); cls.zero(); mx.zero();
-        k_plan_count<G><<<grid_for(n * G, 256), 256, 0, r.stream>>>(d.off.p, d.nbr.p, d.dplus.p, n, pi, P, cw.p, acc.p);
+        k_plan_count<G><<<grid_for(n * G, 256), 256, 0, r.stream>>>(d.off.p, d.nbr.p, d.dplus.p, n, pi, od, cw.p, acc.p);
         launched();
         tr.mark("plan: count pass");
         DevBuf<int64_t> nitems(n + 1), seg(n + 1), item_base(n + 1), segbase(n + 1);
         DevBuf<uint8_t> vstate(n);
         PlanParams pp{opt.variant, hub_bits, (long long)opt.hub_min_work,
                       opt.reserved[0] > 0 ? (long long)opt.reserved[0] : 262144ll};
-        k_classify<<<grid_for(n + 1, 256), 256, 0, r.stream>>>(d.off.p, d.nbr.p, n, cw.p, pp, pi, P, nitems.p, seg.p,
+        k_classify<<<grid_for(n + 1, 256), 256, 0, r.stream>>>(d.off.p, d.nbr.p, n, cw.p, pp, pi, od, nitems.p, seg.p,
                                                               cls.p, mx.p, vstate.p);
         launched();
         unsigned long long h_acc[4], h_cls[5];
@@ -693,7 +696,7 @@ TcPlan *build_plan(const Dag &d, const gmsb_tc_options &opt) {
         // against 9.4 ms; the two passes over the tile and the 48 KB of shared cursors per CTA cost more than the
         // returns of the global atomics.)
         k_plan_scatter<G><<<grid_for(n * G, 256), 256, 0, r.stream>>>(
-            d.off.p, d.nbr.p, d.dplus.p, vstate.p, n, cw.p, p->desc.p, opt.variant, opt.gallop_ratio, pi, P, p->m_desc.p,
+            d.off.p, d.nbr.p, d.dplus.p, vstate.p, n, cw.p, p->desc.p, opt.variant, opt.gallop_ratio, pi, od, p->m_desc.p,
             p->m_v.p, p->g_desc.p, p->g_v.p, cursors.p, hub_u.p);
         launched();
         unsigned long long h_cur[2];

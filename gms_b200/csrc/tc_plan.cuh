@@ -5,6 +5,7 @@
 #pragma once
 #include "common.cuh"
 #include "orient.cuh"
+#include "owner.cuh"
 
 namespace gmsb {
 
@@ -25,12 +26,6 @@ struct Item {            // one CTA work unit: a slice of hub v's incoming descr
     int64_t begin;
     int32_t pad[2];
 };
-
-// owner of position d of a deal among P devices: 0 1 .. P-1 P-1 .. 1 0 0 1 ..
-__host__ __device__ inline int snake_owner(int d, int P) {
-    const int r = d % (2 * P);
-    return r < P ? r : 2 * P - 1 - r;
-}
 
 struct TcPlan {
     gmsb_tc_options opt{};

@@ -15,3 +15,13 @@ def test_lane_core_against_brute_force():
     r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "all checks passed" in r.stdout
+
+
+def test_schedule_owner_deal_fast_form():
+    """tc.cu's owner-of-a-vertex arithmetic (gms_b200/csrc/owner.cuh, __host__ __device__) compiled for the host."""
+    exe = os.path.join(ROOT, "build", "owner_test")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.check_call(["g++", "-std=c++17", "-O2", os.path.join(ROOT, "tests", "cpp", "owner_test.cpp"), "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "all checks passed" in r.stdout
