@@ -151,8 +151,28 @@ def set_device(i):
     _check(lib().gmsb_set_device(i))
 
 
+def _bundled_nccl():
+    """Path of the pip-installed NCCL (the nvidia-nccl wheel PyTorch depends on), or None.  The multi-GPU entry points
+    dlopen libnccl.so.2; a process that later imports torch must get the SAME file, because the loader keeps one object
+    per SONAME (an older system libnccl opened first would leave torch without the symbols it was built against)."""
+    import importlib.util
+    try:
+        spec = importlib.util.find_spec("nvidia.nccl")
+    except (ImportError, ValueError):
+        return None
+    for base in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+        path = os.path.join(base, "lib", "libnccl.so.2")
+        if os.path.exists(path):
+            return path
+    return None
+
+
 def set_devices(ids):
     """The devices of the *_multi entry points (one process, several GPUs); ids[0] becomes the primary device."""
+    if len(ids) > 1 and not os.environ.get("GMSB_NCCL_LIB"):
+        path = _bundled_nccl()
+        if path:
+            os.environ["GMSB_NCCL_LIB"] = path          # read by the library when it first reduces an array (mgpu.cu)
     arr = (C.c_int * len(ids))(*ids)
     _check(lib().gmsb_set_devices(len(ids), arr))
 

@@ -16,6 +16,7 @@
 #include "ops.cuh"
 #include "sort.cuh"
 
+#include <cstdlib>
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -55,7 +56,12 @@ void ensure_nccl() {
     Nccl &n = g_mg.nccl;
     if (!n.comms.empty()) return;
     if (!n.dll) {
-        n.dll = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        // GMSB_NCCL_LIB: the libnccl.so.2 to load.  A host process that also carries its own NCCL (PyTorch bundles one)
+        // must point this at the same file: the loader keeps ONE object per SONAME, so whichever libnccl.so.2 is opened
+        // first is the one everybody gets, and an older system copy loaded here would starve a later `import torch` of
+        // symbols.  gms_b200/capi.py: set_devices() sets it to the pip-installed NCCL when there is one.
+        const char *path = getenv("GMSB_NCCL_LIB");
+        n.dll = dlopen(path && *path ? path : "libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
         if (!n.dll) throw Error(GMSB_ERR_UNSUPPORTED, std::string("libnccl.so.2 could not be loaded: ") + dlerror());
         auto sym = [&](const char *name) {
             void *p = dlsym(n.dll, name);
