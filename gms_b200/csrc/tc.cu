@@ -258,11 +258,13 @@ k_plan_scatter(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, con
 // Order key of an item: window class, then the L2 tile its suffixes start in (tile-major order keeps the lists that
 // concurrently running CTAs stream inside the L2), then heaviest vertex first.  Window classes: 0 = NEAR (everything
 // after v, up to n-1, fits the small window: no element can fall outside the bitmap), 1 = small window, 2 = wide.
-// The tile is derived from the slice's position inside v's descriptor segment (descriptors arrive in roughly
-// ascending u), not from the descriptors themselves: their order inside a class depends on the order of the atomics
-// of the scatter pass, and the item order has to be the same on every device that builds this schedule.
+// Two ways to name the tile (gmsb_tc_options.reserved[1]): from the slice's position inside v's descriptor segment
+// (descriptors arrive in roughly ascending u; round 1's rule, when every device had to derive the same item order
+// without looking at descriptors whose order depends on the scatter pass's atomics), or — addr_shift > 0 — from where
+// the slice's first long suffix actually starts in the neighbour array (every device orders its own share now).
 constexpr int kNearWords = kSmallWindowBytes / 4 - 1;
-__global__ void k_item_keys(const Item *__restrict__ items, int64_t cnt, int64_t n, int64_t ntiles,
+__global__ void k_item_keys(const Item *__restrict__ items, int64_t cnt, int64_t n, int64_t ntiles, int addr_shift,
+                            const uint64_t *__restrict__ desc,
                             const int64_t *__restrict__ nitems, const int64_t *__restrict__ item_base,
                             const eid_t *__restrict__ off, const vid_t *__restrict__ nbr,
                             uint64_t *__restrict__ keys, unsigned long long *__restrict__ cls_count /* 3 */,
@@ -270,7 +272,12 @@ __global__ void k_item_keys(const Item *__restrict__ items, int64_t cnt, int64_t
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < cnt; i += (int64_t)gridDim.x * blockDim.x) {
         const Item it = items[i];
         const int64_t k = nitems[it.v], j = i - item_base[it.v];
-        const uint64_t tile = (uint64_t)(j * ntiles / k);
+        uint64_t tile = (uint64_t)(j * ntiles / k);
+        if (addr_shift > 0) {
+            // the long suffixes carry the work: first descriptor of the longest class present in the slice
+            const int first = it.n1 < it.count ? it.n1 : (it.n0 < it.count ? it.n0 : 0);
+            tile = (desc[it.begin + first] >> kLenBits) >> addr_shift;
+        }
         int words = (int)(((int64_t)nbr[off[it.v + 1] - 1] - it.v + 31) >> 5);
         // a NEAR window starts at the multiple of 32 at or below v + 1 and holds every id up to n - 1
         const int64_t reach_words = ((n - 1 - (((int64_t)it.v + 1) & ~int64_t(31))) >> 5) + 1;
@@ -709,14 +716,17 @@ TcPlan *build_plan(const Dag &d, const gmsb_tc_options &opt) {
             // order: tile-major, heaviest first inside a tile
             DevBuf<uint64_t> ik(p->n_items), ik2(p->n_items);
             DevBuf<Item> items2(p->n_items);
-            const int tile_shift = opt.reserved[1] > 0 ? opt.reserved[1] : (opt.reserved[1] < 0 ? 0 : 24);
+            // reserved[1]: 0 = default; < 0 = no tiles; 1..63 = positional tiles of 2^x slots; 64 + x = address tiles
+            const int knob = opt.reserved[1];
+            const int addr_shift = knob >= 64 ? knob - 64 : 0;
+            const int tile_shift = knob >= 64 ? 0 : (knob > 0 ? knob : (knob < 0 ? 0 : 24));
             const int64_t ntiles = tile_shift > 0 ? std::max<int64_t>(1, (m + (int64_t(1) << tile_shift) - 1) >> tile_shift) : 1;
             DevBuf<unsigned long long> ccnt(3);
             DevBuf<int> cwords(3);
             ccnt.zero(); cwords.zero();
-            k_item_keys<<<grid_for(p->n_items, 256), 256, 0, r.stream>>>(p->items.p, p->n_items, n, ntiles, nitems.p,
-                                                                        item_base.p, d.off.p, d.nbr.p, ik.p, ccnt.p,
-                                                                        cwords.p);
+            k_item_keys<<<grid_for(p->n_items, 256), 256, 0, r.stream>>>(p->items.p, p->n_items, n, ntiles, addr_shift,
+                                                                        p->desc.p, nitems.p, item_base.p, d.off.p,
+                                                                        d.nbr.p, ik.p, ccnt.p, cwords.p);
             launched();
             unsigned long long h_cc[3];
             ccnt.download(h_cc, 3);
