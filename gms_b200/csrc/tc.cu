@@ -103,6 +103,39 @@ k_plan_count(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, const
     }
 }
 
+// The same pass as an element-wise stream over the edge slots, for DAGs that carry Dag::spos (position and suffix
+// length per slot, written when the rows were moved into place): no row is walked, so a device that owns 1/P of the
+// closing vertices pays for a coalesced read of the neighbour array plus 1/P of the gathers and atomics — the row walk
+// costs the same whatever share is kept.
+__global__ void __launch_bounds__(256)
+k_plan_count_flat(const vid_t *__restrict__ nbr, const uint32_t *__restrict__ spos, const int32_t *__restrict__ dplus,
+                  int64_t m, int64_t n, int part_index, OwnerDeal od, unsigned long long *__restrict__ cw /* 3n */,
+                  unsigned long long *__restrict__ acc) {
+    unsigned long long deg2 = 0, wedges = 0, kept = 0, ku = 0;
+    for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < m; s += (int64_t)gridDim.x * blockDim.x) {
+        const vid_t v = nbr[s];
+        if (od.parts > 1 && plan_owner(v, n, od) != part_index) continue;
+        const uint32_t sp = spos[s];
+        const eid_t len = (eid_t)(sp & 0xffffu);
+        const unsigned long long du = (unsigned long long)(sp >> 16) + (unsigned long long)len + 1ull;
+        const int dv = dplus[v];
+        deg2 += du + (unsigned long long)dv;
+        if (len > 0 && dv > 0) {
+            atomicAdd(&cw[3 * (int64_t)v + len_class(len)], (1ull << kCntShift) | (unsigned long long)len);
+            wedges += (unsigned long long)len; kept++; ku += du;
+        }
+    }
+    for (int o = 16; o; o >>= 1) {
+        deg2 += __shfl_xor_sync(0xffffffffu, deg2, o);
+        wedges += __shfl_xor_sync(0xffffffffu, wedges, o);
+        kept += __shfl_xor_sync(0xffffffffu, kept, o);
+        ku += __shfl_xor_sync(0xffffffffu, ku, o);
+    }
+    if ((threadIdx.x & 31) == 0 && deg2) {
+        atomicAdd(&acc[0], deg2); atomicAdd(&acc[1], wedges); atomicAdd(&acc[2], kept); atomicAdd(&acc[3], ku);
+    }
+}
+
 struct PlanParams {
     int variant;
     int hub_bits;
@@ -249,6 +282,51 @@ k_plan_scatter(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, con
                 const unsigned long long i = act.shfl(base, 0) + act.thread_rank();
                 m_desc[i] = ds; m_v[i] = v;
             }
+        }
+    }
+    for (int o = 16; o; o >>= 1) hub_u += __shfl_xor_sync(0xffffffffu, hub_u, o);
+    if ((threadIdx.x & 31) == 0 && hub_u) atomicAdd(&acc[0], hub_u);
+}
+
+// element-wise form of the scatter pass (see k_plan_count_flat); descriptors reach their segments in ascending slot order
+__global__ void __launch_bounds__(256)
+k_plan_scatter_flat(const vid_t *__restrict__ nbr, const uint32_t *__restrict__ spos, const int32_t *__restrict__ dplus,
+                    const uint8_t *__restrict__ vstate, int64_t m, int64_t n, unsigned long long *__restrict__ pos /* 3n */,
+                    uint64_t *__restrict__ desc, int variant, int ratio, int part_index, OwnerDeal od,
+                    uint64_t *__restrict__ m_desc, vid_t *__restrict__ m_v, uint64_t *__restrict__ g_desc,
+                    vid_t *__restrict__ g_v, unsigned long long *__restrict__ cursors /* [0]=merge [1]=gallop */,
+                    unsigned long long *__restrict__ acc /* [0] = sum of d+(u) over the own hub edges */) {
+    namespace cg = cooperative_groups;
+    unsigned long long hub_u = 0;
+    for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < m; s += (int64_t)gridDim.x * blockDim.x) {
+        const vid_t v = nbr[s];
+        if (od.parts > 1 && plan_owner(v, n, od) != part_index) continue;
+        const uint32_t sp = spos[s];
+        const eid_t len = (eid_t)(sp & 0xffffu);
+        if (len <= 0) continue;
+        const uint8_t state = vstate[v];
+        if (state == kDead) continue;
+        const uint64_t ds = ((uint64_t)(s + 1) << kLenBits) | (uint64_t)len;
+        if (state == kHub) {
+            hub_u += (unsigned long long)(sp >> 16) + (unsigned long long)len + 1ull;
+            desc[atomicAdd(&pos[3 * (int64_t)v + len_class(len)], 1ull)] = ds;
+            continue;
+        }
+        const long long a = (long long)len, dv = dplus[v];
+        const long long lo = a < dv ? a : dv, hi = a < dv ? dv : a;
+        const bool gallop = variant == GMSB_TC_GALLOP || (variant != GMSB_TC_MERGE && hi >= (long long)ratio * lo);
+        if (gallop) {
+            cg::coalesced_group act = cg::coalesced_threads();
+            unsigned long long base = 0;
+            if (act.thread_rank() == 0) base = atomicAdd(&cursors[1], (unsigned long long)act.size());
+            const unsigned long long i = act.shfl(base, 0) + act.thread_rank();
+            g_desc[i] = ds; g_v[i] = v;
+        } else {
+            cg::coalesced_group act = cg::coalesced_threads();
+            unsigned long long base = 0;
+            if (act.thread_rank() == 0) base = atomicAdd(&cursors[0], (unsigned long long)act.size());
+            const unsigned long long i = act.shfl(base, 0) + act.thread_rank();
+            m_desc[i] = ds; m_v[i] = v;
         }
     }
     for (int o = 16; o; o >>= 1) hub_u += __shfl_xor_sync(0xffffffffu, hub_u, o);
@@ -660,7 +738,14 @@ TcPlan *build_plan(const Dag &d, const gmsb_tc_options &opt) {
         DevBuf<unsigned long long> cw(3 * (size_t)n), acc(4), cls(5);
         DevBuf<int> mx(2);
         cw.zero(); acc.zero(); cls.zero(); mx.zero();
-        k_plan_count<G><<<grid_for(n * G, 256), 256, 0, r.stream>>>(d.off.p, d.nbr.p, d.dplus.p, n, pi, od, cw.p, acc.p);
+        // element-wise passes when the DAG carries per-slot positions (max d+ < 65536), row walks otherwise;
+        // reserved[3] == 2 forces the row walks (A/B runs)
+        const bool flat = d.spos.p != nullptr && opt.reserved[3] != 2;
+        if (flat)
+            k_plan_count_flat<<<grid_for(m, 256), 256, 0, r.stream>>>(d.nbr.p, d.spos.p, d.dplus.p, m, n, pi, od, cw.p,
+                                                                     acc.p);
+        else
+            k_plan_count<G><<<grid_for(n * G, 256), 256, 0, r.stream>>>(d.off.p, d.nbr.p, d.dplus.p, n, pi, od, cw.p, acc.p);
         launched();
         tr.mark("plan: count pass");
         DevBuf<int64_t> nitems(n + 1), seg(n + 1), item_base(n + 1), segbase(n + 1);
@@ -702,9 +787,14 @@ TcPlan *build_plan(const Dag &d, const gmsb_tc_options &opt) {
         // ATOM per non-empty counter and tile instead of one per edge — was measured slower at scale 24: 14.8 ms
         // against 9.4 ms; the two passes over the tile and the 48 KB of shared cursors per CTA cost more than the
         // returns of the global atomics.)
-        k_plan_scatter<G><<<grid_for(n * G, 256), 256, 0, r.stream>>>(
-            d.off.p, d.nbr.p, d.dplus.p, vstate.p, n, cw.p, p->desc.p, opt.variant, opt.gallop_ratio, pi, od, p->m_desc.p,
-            p->m_v.p, p->g_desc.p, p->g_v.p, cursors.p, hub_u.p);
+        if (flat)
+            k_plan_scatter_flat<<<grid_for(m, 256), 256, 0, r.stream>>>(
+                d.nbr.p, d.spos.p, d.dplus.p, vstate.p, m, n, cw.p, p->desc.p, opt.variant, opt.gallop_ratio, pi, od,
+                p->m_desc.p, p->m_v.p, p->g_desc.p, p->g_v.p, cursors.p, hub_u.p);
+        else
+            k_plan_scatter<G><<<grid_for(n * G, 256), 256, 0, r.stream>>>(
+                d.off.p, d.nbr.p, d.dplus.p, vstate.p, n, cw.p, p->desc.p, opt.variant, opt.gallop_ratio, pi, od,
+                p->m_desc.p, p->m_v.p, p->g_desc.p, p->g_v.p, cursors.p, hub_u.p);
         launched();
         unsigned long long h_cur[2];
         cursors.download(h_cur, 2);

@@ -19,6 +19,8 @@ def main():
     ap.add_argument("--rmat-a", type=float, default=0.57)
     ap.add_argument("--parts", default="1,2,4,8")
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--row-walk", action="store_true", help="force the row-walking schedule passes (A/B against the "
+                                                            "element-wise ones)")
     args = ap.parse_args()
     G.set_device(0)
     a = args.rmat_a
@@ -31,7 +33,7 @@ def main():
         for p in range(P):
             best = None
             for _ in range(args.reps):
-                c, st = g.tc_total_ex(part_index=p, part_count=P, reuse_plan=2)
+                c, st = g.tc_total_ex(part_index=p, part_count=P, reuse_plan=2, merge_impl=2 if args.row_walk else 0)
                 if best is None or st["ms_orient"] + st["ms_count"] < best["ms_orient"] + best["ms_count"]:
                     best = st
             tri += c
@@ -40,7 +42,7 @@ def main():
             bitmap.append(round(best["ms_bitmap"], 3))
         assert tri == total, (P, tri, total)
         step = [s + c for s, c in zip(sched, count)]
-        print(json.dumps({"scale": args.scale, "rmat_a": a, "parts": P, "triangles": tri, "edges_scheduled": edges,
+        print(json.dumps({"scale": args.scale, "rmat_a": a, "row_walk": args.row_walk, "parts": P, "triangles": tri, "edges_scheduled": edges,
                           "schedule_ms": sched, "count_ms": count, "bitmap_ms": bitmap,
                           "max_step_ms": round(max(step), 3), "mean_step_ms": round(sum(step) / P, 3),
                           "max_count_ms": max(count), "mean_count_ms": round(sum(count) / P, 3)}), flush=True)
