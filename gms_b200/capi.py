@@ -334,7 +334,8 @@ class Graph:
     def tc_total_ex(self, variant="auto", part_index=0, part_count=1, reuse_plan=False, hub_bitmap_bits=0,
                     gallop_ratio=0, hub_min_work=0, item_cost=0, tile_shift=0, cta_shape=0, merge_impl=0):
         """item_cost / tile_shift / cta_shape / merge_impl are tuning knobs carried in gmsb_tc_options.reserved[0..3]
-        (merge_impl = 1: the block-compare kernel for the balanced light pairs instead of the merge path; measured slower)."""
+        (merge_impl = 1: the block-compare kernel for the balanced light pairs instead of the merge path, measured slower;
+        2 / 3: force the row-walking / the element-wise form of the schedule's edge passes)."""
         opt = TcOptions(TC_VARIANTS[variant], part_index, part_count, int(reuse_plan), hub_bitmap_bits, gallop_ratio,
                         hub_min_work, (C.c_int32 * 4)(item_cost, tile_shift, cta_shape, merge_impl))
         out, st = C.c_uint64(0), TcStats()

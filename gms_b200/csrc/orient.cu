@@ -421,13 +421,12 @@ __global__ void k_counts_by_rank(const int32_t *__restrict__ dold, const vid_t *
 // (5) row move: the len[u] elements at src[src_start[u] ..) go to dst[dst_start ..) for every vertex u of the range,
 // where dst_start = dst_off[rank[u]] (BY_RANK: rows into their place in the oriented CSR) or dst_off[u - u_begin] (rows
 // packed in original-id order: the piece a device hands to the others).  Warp chunks as above: 32 rows per warp, their
-// elements streamed 32 at a time.  spos (optional, rows shorter than 65536): per destination slot, the element's
-// position in its row and the number of elements after it.
+// elements streamed 32 at a time.
 template <bool BY_RANK>
 __global__ void __launch_bounds__(256)
 k_move_rows(const eid_t *__restrict__ src_start, const int32_t *__restrict__ len, const vid_t *__restrict__ src,
             int64_t u_begin, int64_t u_end, const eid_t *__restrict__ dst_off, const vid_t *__restrict__ rank,
-            vid_t *__restrict__ dst, uint32_t *__restrict__ spos) {
+            vid_t *__restrict__ dst) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -451,11 +450,7 @@ k_move_rows(const eid_t *__restrict__ src_start, const int32_t *__restrict__ len
             const int owner = chunk_owner(rel, act ? i : total - 1);
             const int j = i - __shfl_sync(0xffffffffu, rel, owner);
             const eid_t so = __shfl_sync(0xffffffffu, ss, owner), dofs = __shfl_sync(0xffffffffu, dd, owner);
-            const int oc = __shfl_sync(0xffffffffu, c, owner);
-            if (act) {
-                dst[dofs + j] = src[so + j];
-                if (spos) spos[dofs + j] = ((uint32_t)j << 16) | (uint32_t)(oc - 1 - j);
-            }
+            if (act) dst[dofs + j] = src[so + j];
         }
     }
 }
@@ -612,7 +607,7 @@ static int on_chip_sort_cap() {
 
 // every range has been through orient_rows_range: big lists, offsets, remaining sorts, rows into rank order
 void orient_rows_finish(const Graph &g, const vid_t *rank_dev, OrientRows &w, DevBuf<eid_t> &doff, DevBuf<vid_t> &dnbr,
-                        int64_t *m_out, int *max_dplus, DevBuf<int32_t> *dplus, DevBuf<uint32_t> *spos, PhaseTrace &tr) {
+                        int64_t *m_out, int *max_dplus, DevBuf<int32_t> *dplus, PhaseTrace &tr) {
     Runtime &r = rt();
     const int64_t n = g.n;
     orient_rows_big(g, rank_dev, w);
@@ -627,9 +622,8 @@ void orient_rows_finish(const Graph &g, const vid_t *rank_dev, OrientRows &w, De
         // lists sorted on chip: registers (<= 32) or shared memory; then one streaming pass moves the rows into place
         orient_rows_sort(w);
         tr.mark("orient: list sorts");
-        if (spos) spos->alloc(m);                      // maxd <= kSortCap < 65536 on this path
         k_move_rows<true><<<grid_for(n, 256), 256, 0, r.stream>>>(g.off.p, w.dold.p, w.trow.p, 0, n, doff.p, rank_dev,
-                                                                 dnbr.p, spos ? spos->p : nullptr);
+                                                                 dnbr.p);
         launched();
         tr.mark("orient: rows into rank order");
     } else {
@@ -643,12 +637,12 @@ void orient_rows_finish(const Graph &g, const vid_t *rank_dev, OrientRows &w, De
 }
 
 void orient_by_rank(const Graph &g, const vid_t *rank_dev, DevBuf<eid_t> &doff, DevBuf<vid_t> &dnbr, int64_t *m_out,
-                    int *max_dplus, DevBuf<int32_t> *dplus, DevBuf<uint32_t> *spos) {
+                    int *max_dplus, DevBuf<int32_t> *dplus) {
     PhaseTrace tr("GMSB_TC_TRACE");
     OrientRows w;
     orient_rows_begin(g, w);
     orient_rows_range(g, rank_dev, w, 0, g.n);
-    orient_rows_finish(g, rank_dev, w, doff, dnbr, m_out, max_dplus, dplus, spos, tr);
+    orient_rows_finish(g, rank_dev, w, doff, dnbr, m_out, max_dplus, dplus, tr);
     GMSB_CUDA(cudaStreamSynchronize(rt().stream));      // the work buffers are released when this returns
 }
 
@@ -665,7 +659,7 @@ void orient_pipeline_range(const Graph &g, OrientPipeline &p, int64_t u_begin, i
 }
 void orient_pipeline_finish(const Graph &g, OrientPipeline &p) {
     PhaseTrace tr("GMSB_TC_TRACE");
-    orient_rows_finish(g, p.d->rank.p, p.w, p.d->off, p.d->nbr, &p.d->m, &p.d->max_dplus, &p.d->dplus, &p.d->spos, tr);
+    orient_rows_finish(g, p.d->rank.p, p.w, p.d->off, p.d->nbr, &p.d->m, &p.d->max_dplus, &p.d->dplus, tr);
     GMSB_CUDA(cudaStreamSynchronize(rt().stream));
     p.w = OrientRows();
 }
@@ -694,7 +688,7 @@ void orient_piece_export(const Graph &g, OrientRows &w, int64_t u0, int64_t u1, 
     Runtime &r = rt();
     if (u1 > u0) {
         k_move_rows<false><<<grid_for(u1 - u0, 256), 256, 0, r.stream>>>(g.off.p, w.dold.p, w.trow.p, u0, u1, piece_off.p,
-                                                                        nullptr, piece_dst, nullptr);
+                                                                        nullptr, piece_dst);
         launched();
         GMSB_CUDA(cudaMemcpyAsync(dplus_all + u0, w.dold.p + u0, sizeof(int32_t) * (size_t)(u1 - u0),
                                   cudaMemcpyDeviceToDevice, r.stream));
@@ -717,9 +711,7 @@ void dag_from_pieces(Dag &d, const int32_t *dplus_all, const vid_t *pieces, int6
     pc.parts = parts;
     for (int i = 0; i <= parts; ++i) pc.cut[i] = cut[i];
     k_piece_starts<<<grid_for(n, 256), 256, 0, r.stream>>>(scan.p, n, pc, stride, src_start.p); launched();
-    if (d.max_dplus < 65536) d.spos.alloc(d.m);
-    k_move_rows<true><<<grid_for(n, 256), 256, 0, r.stream>>>(src_start.p, len.p, pieces, 0, n, d.off.p, d.rank.p, d.nbr.p,
-                                                             d.spos.p);
+    k_move_rows<true><<<grid_for(n, 256), 256, 0, r.stream>>>(src_start.p, len.p, pieces, 0, n, d.off.p, d.rank.p, d.nbr.p);
     launched();
     GMSB_CUDA(cudaStreamSynchronize(r.stream));
 }
@@ -732,7 +724,7 @@ Dag *build_degree_dag(const Graph &g) {
         PhaseTrace tr("GMSB_TC_TRACE");
         degree_order(g, d->order, d->rank, &d->max_deg);
         tr.mark("orient: degree order");
-        orient_by_rank(g, d->rank.p, d->off, d->nbr, &d->m, &d->max_dplus, &d->dplus, &d->spos);
+        orient_by_rank(g, d->rank.p, d->off, d->nbr, &d->m, &d->max_dplus, &d->dplus);
     } catch (...) { delete d; throw; }
     return d;
 }

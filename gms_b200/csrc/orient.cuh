@@ -19,15 +19,15 @@ struct Dag {
     DevBuf<eid_t> off;           // n+1
     DevBuf<vid_t> nbr;           // m, ascending within each list, all entries > owner
     DevBuf<int32_t> dplus;       // n: d+(v) as a compact array (random reads of it stay inside the L2)
-    DevBuf<uint32_t> spos;       // m (only while max d+ < 65536): per slot (position in its list << 16) | elements after
-                                 // it — lets the schedule passes stream the edges without walking rows (tc.cu)
+    DevBuf<uint32_t> spos;       // m, built on demand by the triangle schedule (tc.cu: ensure_slot_positions): per slot
+                                 // (position in its list << 16) | elements after it
     TcPlan *plan = nullptr;      // cached schedule for the triangle kernels
     ~Dag();
 };
 
 void degree_order(const Graph &g, DevBuf<vid_t> &order, DevBuf<vid_t> &rank, int64_t *max_deg = nullptr);
 void orient_by_rank(const Graph &g, const vid_t *rank_dev, DevBuf<eid_t> &doff, DevBuf<vid_t> &dnbr, int64_t *m_out,
-                    int *max_dplus, DevBuf<int32_t> *dplus = nullptr, DevBuf<uint32_t> *spos = nullptr);
+                    int *max_dplus, DevBuf<int32_t> *dplus = nullptr);
 Dag *build_degree_dag(const Graph &g);
 // The orientation passes work on vertex ranges of the input and write each row's survivors to the front of the row's
 // own slot range (orient.cu); this is their state between calls.

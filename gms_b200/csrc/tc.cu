@@ -103,26 +103,51 @@ k_plan_count(const eid_t *__restrict__ off, const vid_t *__restrict__ nbr, const
     }
 }
 
-// The same pass as an element-wise stream over the edge slots, for DAGs that carry Dag::spos (position and suffix
-// length per slot, written when the rows were moved into place): no row is walked, so a device that owns 1/P of the
-// closing vertices pays for a coalesced read of the neighbour array plus 1/P of the gathers and atomics — the row walk
-// costs the same whatever share is kept.
+// The same pass as an element-wise stream over the edge slots, given Dag::spos (position and suffix length per slot,
+// built once per DAG by k_slot_positions): no row is walked, so a device that owns 1/P of the closing vertices pays for
+// a coalesced read of two arrays plus 1/P of the gathers and atomics.  Measured at scale 24
+// (profiles/r2o_partition_balance.jsonl): schedule of one part of 8 3.1-3.3 ms against 3.8-3.9 ms with the row walks,
+// but 11.4 against 10.6 ms for the whole schedule — so the element-wise form is used from 4 parts on.
+__global__ void __launch_bounds__(256)
+k_slot_positions(const eid_t *__restrict__ off, int64_t n, uint32_t *__restrict__ spos) {
+    constexpr int G = 8;
+    const int sub = threadIdx.x % G;
+    const int64_t grp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / G;
+    const int64_t ngrp = ((int64_t)gridDim.x * blockDim.x) / G;
+    for (int64_t u = grp; u < n; u += ngrp) {
+        const eid_t b = off[u], e = off[u + 1];
+        for (eid_t s = b + sub; s < e; s += G) spos[s] = ((uint32_t)(s - b) << 16) | (uint32_t)(e - s - 1);
+    }
+}
+
+constexpr int kFlatUnroll = 4;
 __global__ void __launch_bounds__(256)
 k_plan_count_flat(const vid_t *__restrict__ nbr, const uint32_t *__restrict__ spos, const int32_t *__restrict__ dplus,
                   int64_t m, int64_t n, int part_index, OwnerDeal od, unsigned long long *__restrict__ cw /* 3n */,
                   unsigned long long *__restrict__ acc) {
     unsigned long long deg2 = 0, wedges = 0, kept = 0, ku = 0;
-    for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < m; s += (int64_t)gridDim.x * blockDim.x) {
-        const vid_t v = nbr[s];
-        if (od.parts > 1 && plan_owner(v, n, od) != part_index) continue;
-        const uint32_t sp = spos[s];
-        const eid_t len = (eid_t)(sp & 0xffffu);
-        const unsigned long long du = (unsigned long long)(sp >> 16) + (unsigned long long)len + 1ull;
-        const int dv = dplus[v];
-        deg2 += du + (unsigned long long)dv;
-        if (len > 0 && dv > 0) {
-            atomicAdd(&cw[3 * (int64_t)v + len_class(len)], (1ull << kCntShift) | (unsigned long long)len);
-            wedges += (unsigned long long)len; kept++; ku += du;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t s0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s0 < m; s0 += kFlatUnroll * stride) {
+        vid_t vs[kFlatUnroll];
+        uint32_t sps[kFlatUnroll];
+#pragma unroll
+        for (int q = 0; q < kFlatUnroll; ++q) {                       // independent streaming loads first
+            const int64_t s = s0 + q * stride;
+            vs[q] = s < m ? nbr[s] : -1;
+            sps[q] = s < m ? spos[s] : 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < kFlatUnroll; ++q) {
+            const vid_t v = vs[q];
+            if (v < 0 || (od.parts > 1 && plan_owner(v, n, od) != part_index)) continue;
+            const eid_t len = (eid_t)(sps[q] & 0xffffu);
+            const unsigned long long du = (unsigned long long)(sps[q] >> 16) + (unsigned long long)len + 1ull;
+            const int dv = dplus[v];
+            deg2 += du + (unsigned long long)dv;
+            if (len > 0 && dv > 0) {
+                atomicAdd(&cw[3 * (int64_t)v + len_class(len)], (1ull << kCntShift) | (unsigned long long)len);
+                wedges += (unsigned long long)len; kept++; ku += du;
+            }
         }
     }
     for (int o = 16; o; o >>= 1) {
@@ -298,35 +323,46 @@ k_plan_scatter_flat(const vid_t *__restrict__ nbr, const uint32_t *__restrict__ 
                     unsigned long long *__restrict__ acc /* [0] = sum of d+(u) over the own hub edges */) {
     namespace cg = cooperative_groups;
     unsigned long long hub_u = 0;
-    for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < m; s += (int64_t)gridDim.x * blockDim.x) {
-        const vid_t v = nbr[s];
-        if (od.parts > 1 && plan_owner(v, n, od) != part_index) continue;
-        const uint32_t sp = spos[s];
-        const eid_t len = (eid_t)(sp & 0xffffu);
-        if (len <= 0) continue;
-        const uint8_t state = vstate[v];
-        if (state == kDead) continue;
-        const uint64_t ds = ((uint64_t)(s + 1) << kLenBits) | (uint64_t)len;
-        if (state == kHub) {
-            hub_u += (unsigned long long)(sp >> 16) + (unsigned long long)len + 1ull;
-            desc[atomicAdd(&pos[3 * (int64_t)v + len_class(len)], 1ull)] = ds;
-            continue;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t s0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s0 < m; s0 += kFlatUnroll * stride) {
+        vid_t vs[kFlatUnroll];
+        uint32_t sps[kFlatUnroll];
+#pragma unroll
+        for (int q = 0; q < kFlatUnroll; ++q) {
+            const int64_t s = s0 + q * stride;
+            vs[q] = s < m ? nbr[s] : -1;
+            sps[q] = s < m ? spos[s] : 0u;
         }
-        const long long a = (long long)len, dv = dplus[v];
-        const long long lo = a < dv ? a : dv, hi = a < dv ? dv : a;
-        const bool gallop = variant == GMSB_TC_GALLOP || (variant != GMSB_TC_MERGE && hi >= (long long)ratio * lo);
-        if (gallop) {
-            cg::coalesced_group act = cg::coalesced_threads();
-            unsigned long long base = 0;
-            if (act.thread_rank() == 0) base = atomicAdd(&cursors[1], (unsigned long long)act.size());
-            const unsigned long long i = act.shfl(base, 0) + act.thread_rank();
-            g_desc[i] = ds; g_v[i] = v;
-        } else {
-            cg::coalesced_group act = cg::coalesced_threads();
-            unsigned long long base = 0;
-            if (act.thread_rank() == 0) base = atomicAdd(&cursors[0], (unsigned long long)act.size());
-            const unsigned long long i = act.shfl(base, 0) + act.thread_rank();
-            m_desc[i] = ds; m_v[i] = v;
+#pragma unroll
+        for (int q = 0; q < kFlatUnroll; ++q) {
+            const vid_t v = vs[q];
+            const int64_t s = s0 + q * stride;
+            const eid_t len = (eid_t)(sps[q] & 0xffffu);
+            if (v < 0 || len <= 0 || (od.parts > 1 && plan_owner(v, n, od) != part_index)) continue;
+            const uint8_t state = vstate[v];
+            if (state == kDead) continue;
+            const uint64_t ds = ((uint64_t)(s + 1) << kLenBits) | (uint64_t)len;
+            if (state == kHub) {
+                hub_u += (unsigned long long)(sps[q] >> 16) + (unsigned long long)len + 1ull;
+                desc[atomicAdd(&pos[3 * (int64_t)v + len_class(len)], 1ull)] = ds;
+                continue;
+            }
+            const long long a = (long long)len, dv = dplus[v];
+            const long long lo = a < dv ? a : dv, hi = a < dv ? dv : a;
+            const bool gallop = variant == GMSB_TC_GALLOP || (variant != GMSB_TC_MERGE && hi >= (long long)ratio * lo);
+            if (gallop) {
+                cg::coalesced_group act = cg::coalesced_threads();
+                unsigned long long base = 0;
+                if (act.thread_rank() == 0) base = atomicAdd(&cursors[1], (unsigned long long)act.size());
+                const unsigned long long i = act.shfl(base, 0) + act.thread_rank();
+                g_desc[i] = ds; g_v[i] = v;
+            } else {
+                cg::coalesced_group act = cg::coalesced_threads();
+                unsigned long long base = 0;
+                if (act.thread_rank() == 0) base = atomicAdd(&cursors[0], (unsigned long long)act.size());
+                const unsigned long long i = act.shfl(base, 0) + act.thread_rank();
+                m_desc[i] = ds; m_v[i] = v;
+            }
         }
     }
     for (int o = 16; o; o >>= 1) hub_u += __shfl_xor_sync(0xffffffffu, hub_u, o);
@@ -714,7 +750,7 @@ bool same_plan(const gmsb_tc_options &a, const gmsb_tc_options &b) {
     // (reserved[2], reserved[3] pick kernel builds, not the schedule)
 }
 
-TcPlan *build_plan(const Dag &d, const gmsb_tc_options &opt) {
+TcPlan *build_plan(Dag &d, const gmsb_tc_options &opt) {
     Runtime &r = rt();
     auto *p = new TcPlan();
     try {
@@ -738,9 +774,13 @@ TcPlan *build_plan(const Dag &d, const gmsb_tc_options &opt) {
         DevBuf<unsigned long long> cw(3 * (size_t)n), acc(4), cls(5);
         DevBuf<int> mx(2);
         cw.zero(); acc.zero(); cls.zero(); mx.zero();
-        // element-wise passes when the DAG carries per-slot positions (max d+ < 65536), row walks otherwise;
-        // reserved[3] == 2 forces the row walks (A/B runs)
-        const bool flat = d.spos.p != nullptr && opt.reserved[3] != 2;
+        // element-wise passes from 4 parts on (lists shorter than 65536), row walks otherwise;
+        // reserved[3]: 2 forces the row walks, 3 the element-wise form (A/B runs, tests)
+        const bool flat = d.max_dplus < 65536 && opt.reserved[3] != 2 && (opt.part_count >= 4 || opt.reserved[3] == 3);
+        if (flat && d.spos.p == nullptr) {              // once per DAG
+            d.spos.alloc(m);
+            k_slot_positions<<<grid_for(n * 8, 256), 256, 0, r.stream>>>(d.off.p, n, d.spos.p); launched();
+        }
         if (flat)
             k_plan_count_flat<<<grid_for(m, 256), 256, 0, r.stream>>>(d.nbr.p, d.spos.p, d.dplus.p, m, n, pi, od, cw.p,
                                                                      acc.p);
