@@ -394,9 +394,9 @@ def run_ours(args):
     value = m * args.steps / (ms_total * 1e-3)
 
     # ---- e2e: host CSR -> HBM -> orient -> schedule -> count -> result, nothing cached
-    # N = 1: the plain C-ABI call on the host buffers; N > 1: the sharded build (every rank uploads the offsets and its own
-    # vertex range of the neighbour array; h2d counts all ranks)
-    e2e_value, e2e_ms, e2e_steps, e2e_orient, h2d = None, float("nan"), 1, [float("nan")], world * 8 * (n + 1) + 4 * slots
+    # N = 1: the plain C-ABI call on the host buffers; N > 1: the sharded build (every rank uploads 1/N of the offsets and
+    # its own vertex range of the neighbour array; h2d counts all ranks)
+    e2e_value, e2e_ms, e2e_steps, e2e_orient, h2d = None, float("nan"), 1, [float("nan")], 8 * (n + 1) + 4 * slots
     if not args.no_e2e:
         e2e_value, e2e_ms, e2e_steps, e2e_orient = run_e2e(args, G, gd, off_h, nbr_h, n, slots, m, opts, expect, world, dev)
 
@@ -452,8 +452,9 @@ def run_ours(args):
                 "note": ("gmsb_graph_from_csr_ex(GMSB_BUILD_ORIENT) from pinned host memory (upload pipelined with the "
                          "ranking / validation / orientation passes) + gmsb_tc_total_ex with nothing cached + result"
                          if world == 1 else
-                         "gmsb_shard_begin / export / finish from pinned host memory (each rank uploads and orients one "
-                         "vertex range; pieces all-gathered over NVLink) + gmsb_tc_total_ex with nothing cached + result")},
+                         "gmsb_shard_begin / export / finish from pinned host memory (each rank uploads 1/N of the offsets "
+                         "and one vertex range of the neighbour array and orients that range; offsets and finished rows "
+                         "all-gathered over NVLink) + gmsb_tc_total_ex with nothing cached + result")},
     }
 
     if args.no_e2e:

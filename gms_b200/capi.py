@@ -66,7 +66,7 @@ SIGNATURES = {
     "gmsb_graph_from_csr": (C.c_int, [C.c_int64, _i64p, _i32p, C.c_int, C.POINTER(C.c_void_p)]),
     "gmsb_graph_from_csr_ex": (C.c_int, [C.c_int64, _i64p, _i32p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "gmsb_graph_from_csr_device": (C.c_int, [C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
-    "gmsb_shard_begin": (C.c_int, [C.c_int64, _i64p, _i32p, C.c_int, C.c_int, C.POINTER(C.c_void_p),
+    "gmsb_shard_begin": (C.c_int, [C.c_int64, _i64p, _i32p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p),
                                    C.POINTER(C.c_int64)]),
     "gmsb_shard_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "gmsb_shard_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_void_p)]),
@@ -434,11 +434,14 @@ class Shard:
     the vertex range of part `part_index`; the caller exchanges the exported pieces; `finish` returns a Graph that
     answers the triangle entry points."""
 
-    def __init__(self, offsets, nbrs, part_index, part_count):
+    def __init__(self, offsets, nbrs, part_index, part_count, offsets_dev_ptr=None):
+        """offsets_dev_ptr: device pointer of the complete int64 offsets (e.g. after an all-gather), or None to upload
+        them from `offsets`."""
         offsets = np.ascontiguousarray(offsets, np.int64)
         h, plen = C.c_void_p(), C.c_int64()
-        _check(lib().gmsb_shard_begin(len(offsets) - 1, offsets, _ids(nbrs), int(part_index), int(part_count),
-                                      C.byref(h), C.byref(plen)))
+        _check(lib().gmsb_shard_begin(len(offsets) - 1, offsets, _ids(nbrs),
+                                      C.c_void_p(offsets_dev_ptr) if offsets_dev_ptr else None, int(part_index),
+                                      int(part_count), C.byref(h), C.byref(plen)))
         self.h, self.piece_len = h, plen.value
 
     def export(self, piece_ptr, dplus_all_ptr):

@@ -262,11 +262,11 @@ GMSB_API int gmsb_graph_from_csr_device(int64_t n, const int64_t *off, const int
     });
 }
 // sharded construction of the oriented representation (graph_build.cu: shard_*)
-GMSB_API int gmsb_shard_begin(int64_t n, const int64_t *off, const int32_t *nbr, int part_index, int part_count,
-                              gmsb_shard_t *out, int64_t *piece_len) {
+GMSB_API int gmsb_shard_begin(int64_t n, const int64_t *off, const int32_t *nbr, const int64_t *off_dev, int part_index,
+                              int part_count, gmsb_shard_t *out, int64_t *piece_len) {
     return guarded([&] {
         GMSB_REQUIRE(out, "null output handle");
-        *out = reinterpret_cast<gmsb_shard_t>(shard_begin(n, off, nbr, part_index, part_count, piece_len));
+        *out = reinterpret_cast<gmsb_shard_t>(shard_begin(n, off, nbr, off_dev, part_index, part_count, piece_len));
     });
 }
 GMSB_API int gmsb_shard_export(gmsb_shard_t s, int32_t *piece_dev, int32_t *dplus_all_dev) {

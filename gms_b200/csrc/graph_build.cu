@@ -217,16 +217,24 @@ struct UploadStreams {
 // Uploads the offsets and the neighbour slots of the vertex range [u0, u1) (the whole graph, or one device's share of
 // it) in `chunks` pieces of about equal slot counts and runs the orientation passes on every piece as it lands.
 // flags[0] is raised by an id outside [0, n); desc[1] counts the descents between consecutive slots.
+// off_dev (optional): the complete offsets array already on this device (ordered on the library stream) — then only the
+// few entries the host needs for the cuts are read from `off`.
 void upload_and_orient_range(Graph *g, OrientPipeline &pipe, UploadStreams &st, const eid_t *off, const vid_t *nbr,
-                             int64_t u0, int64_t u1, int chunks, DevBuf<int> &flags, DevBuf<unsigned long long> &desc) {
+                             int64_t u0, int64_t u1, int chunks, DevBuf<int> &flags, DevBuf<unsigned long long> &desc,
+                             const eid_t *off_dev = nullptr) {
     Runtime &r = rt();
     const int64_t n = g->n;
     const eid_t last = g->slots;
     GMSB_CUDA(cudaStreamCreateWithFlags(&st.copy, cudaStreamNonBlocking));
     // allocations above may have been served from blocks whose last use is still queued on the library stream
     GMSB_CUDA(cudaStreamSynchronize(r.stream));
-    GMSB_CUDA(cudaMemcpyAsync(g->off.p, off, sizeof(eid_t) * (n + 1), cudaMemcpyHostToDevice, st.copy));
-    cudaEvent_t ev_off = st.mark();
+    cudaEvent_t ev_off = nullptr;
+    if (off_dev) {
+        GMSB_CUDA(cudaMemcpyAsync(g->off.p, off_dev, sizeof(eid_t) * (n + 1), cudaMemcpyDeviceToDevice, r.stream));
+    } else {
+        GMSB_CUDA(cudaMemcpyAsync(g->off.p, off, sizeof(eid_t) * (n + 1), cudaMemcpyHostToDevice, st.copy));
+        ev_off = st.mark();
+    }
     // vertex ranges of about equal slot counts (the host array is only used to pick the cuts: a malformed one is
     // caught by the device check of the offsets below before any range is processed)
     auto clamp = [&](eid_t x) { return x < 0 ? eid_t(0) : (x > last ? last : x); };
@@ -253,7 +261,7 @@ void upload_and_orient_range(Graph *g, OrientPipeline &pipe, UploadStreams &st, 
         ev_chunk.push_back(st.mark());
     }
     // library stream: offsets -> validation -> ranking; then range by range
-    GMSB_CUDA(cudaStreamWaitEvent(r.stream, ev_off, 0));
+    if (ev_off) GMSB_CUDA(cudaStreamWaitEvent(r.stream, ev_off, 0));
     k_check_offsets_only<<<grid_for(n, 256), 256, 0, r.stream>>>(g->off.p, n, last, flags.p); launched();
     GMSB_REQUIRE(flags.get(0) == 0, "graph_from_csr: offsets not monotone or outside the neighbour array");
     orient_pipeline_begin(*g, pipe);
@@ -318,13 +326,15 @@ Graph *graph_from_csr_host_pipelined(int64_t n, const eid_t *off, const vid_t *n
 // ---- sharded construction (one process per device) ----------------------------------------------------------------------
 // Device `part` of `parts` uploads the offsets and the neighbour slots of ITS vertex range only (ranges of about equal
 // slot counts, computed the same way by everyone from the host offsets), orients and sorts those rows, and packs them
-// into a piece.  The caller exchanges the pieces (one all-gather) and the d+ values (one all-reduce of an int32[n] that
+// into a piece.  The offsets are needed in full (the ranking looks at every degree): either every device uploads them
+// (off_dev == nullptr), or the caller uploads 1/parts of them per device, all-gathers and passes the device copy.  The caller exchanges the pieces (one all-gather) and the d+ values (one all-reduce of an int32[n] that
 // every device filled in its own range); shard_finish then moves all rows into rank order.  Per device the host link
 // carries 1/parts of the neighbour array and the orientation passes touch 1/parts of the rows.  The resulting handle
 // holds the oriented representation only (Graph::dag_only): the symmetric lists of the other ranges never arrive.
 Shard::~Shard() { delete d; delete g; }
 
-Shard *shard_begin(int64_t n, const eid_t *off, const vid_t *nbr, int part, int parts, int64_t *piece_len) {
+Shard *shard_begin(int64_t n, const eid_t *off, const vid_t *nbr, const eid_t *off_dev, int part, int parts,
+                   int64_t *piece_len) {
     GMSB_REQUIRE(n >= 0 && off != nullptr && piece_len != nullptr, "shard_begin: bad arguments");
     GMSB_REQUIRE(parts >= 1 && parts <= 64 && part >= 0 && part < parts, "shard_begin: bad partition");
     Runtime &r = rt();
@@ -352,7 +362,7 @@ Shard *shard_begin(int64_t n, const eid_t *off, const vid_t *nbr, int part, int 
         DevBuf<int> flags(1);
         DevBuf<unsigned long long> desc(2);
         flags.zero(); desc.zero();
-        upload_and_orient_range(g, pipe, st, off, nbr, u0, u1, 4, flags, desc);
+        upload_and_orient_range(g, pipe, st, off, nbr, u0, u1, 4, flags, desc, off_dev);
         s->d = pipe.d;
         pipe.d = nullptr;
         GMSB_REQUIRE(flags.get(0) == 0, "graph_from_csr: neighbour id out of range");

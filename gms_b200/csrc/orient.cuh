@@ -73,7 +73,8 @@ struct Shard {
     DevBuf<eid_t> piece_off;            // exclusive scan of d+ over the own range
     ~Shard();
 };
-Shard *shard_begin(int64_t n, const eid_t *off, const vid_t *nbr, int part, int parts, int64_t *piece_len);
+Shard *shard_begin(int64_t n, const eid_t *off, const vid_t *nbr, const eid_t *off_dev, int part, int parts,
+                   int64_t *piece_len);
 void shard_export(Shard &s, vid_t *piece_dev, int32_t *dplus_all_dev);
 Graph *shard_finish(Shard &s, const vid_t *pieces_dev, int64_t piece_stride, const int32_t *dplus_all_dev);
 Graph *graph_from_edgelist_device(int64_t m, const vid_t *src, const vid_t *dst, bool symmetrize);

@@ -10,6 +10,7 @@ over NVLink (`ShardedCsrUpload`), so the host is read once.
 """
 import os
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -71,27 +72,43 @@ def tc_total_sharded(graph, **opts):
 
 
 class ShardedOrientedBuild:
-    """Host CSR -> oriented device graph with the work sharded over the ranks (gmsb_shard_*): rank r uploads and orients
-    the vertex range r of `world` (1/world of the neighbour array over its own host link), the finished rows are
-    all-gathered over NVLink and the d+ values all-reduced, and every rank moves the rows into rank order.  The graph
-    `build()` returns answers the triangle entry points (its symmetric lists are incomplete by construction).
+    """Host CSR -> oriented device graph with the work sharded over the ranks (gmsb_shard_*): rank r uploads 1/world of
+    the offsets (all-gathered over NVLink: the ranking needs every degree) and the neighbour slots of vertex range r of
+    `world`, orients those rows, the finished rows are all-gathered and the d+ values all-reduced, and every rank moves
+    the rows into rank order.  Over the host links go 8(n+1) + 4*slots bytes in total, whatever the number of ranks.
+    The graph `build()` returns answers the triangle entry points (its symmetric lists are incomplete by construction).
     Buffers are allocated once and reused by every `build()`."""
 
     def __init__(self, offsets_host, nbrs_host, device, shard_factory=None):
         self.rank, self.world = (dist.get_rank(), dist.get_world_size()) if dist.is_initialized() else (0, 1)
         self.device = torch.device(device)
         self.shard_factory = shard_factory          # tests drive the exchange on CPU tensors with a stand-in
-        self.off = offsets_host.numpy() if isinstance(offsets_host, torch.Tensor) else offsets_host
+        self.off_t = offsets_host if isinstance(offsets_host, torch.Tensor) else torch.from_numpy(offsets_host)
+        self.off = self.off_t.numpy()
         self.nbr = nbrs_host.numpy() if isinstance(nbrs_host, torch.Tensor) else nbrs_host
         self.n = len(self.off) - 1
         self.dplus = torch.zeros(max(self.n, 1), dtype=torch.int32, device=self.device)
         self.pieces = None
+        self.off_upload = _ShardedArray(self.off_t, self.device, self.rank, self.world) if self.world > 1 else None
+
+    @property
+    def h2d_bytes(self):
+        """Bytes this rank copies host->device per build (its share of the offsets + its vertex range's slots; the
+        latter from the same cuts the library computes)."""
+        if self.world == 1:
+            return 8 * (self.n + 1) + 4 * int(self.off[self.n])
+        last = int(self.off[self.n])
+        cut = [0] + [int(np.searchsorted(self.off[:self.n], last // self.world * i, "left")) for i in range(1, self.world)]
+        cut = list(np.maximum.accumulate(cut)) + [self.n]
+        own = int(self.off[cut[self.rank + 1]] - self.off[cut[self.rank]])
+        return self.off_upload.h2d_bytes + 4 * own
 
     def build(self):
         if self.shard_factory is None:
             from . import capi
             self.shard_factory = capi.Shard
-        shard = self.shard_factory(self.off, self.nbr, self.rank, self.world)
+        off_dev = self.off_upload.upload().data_ptr() if self.off_upload is not None else None
+        shard = self.shard_factory(self.off, self.nbr, self.rank, self.world, offsets_dev_ptr=off_dev)
         stride = max(int(allreduce_max(shard.piece_len, device=self.device)), 1)
         if self.pieces is None or self.pieces.numel() < stride * self.world:
             self.pieces = torch.empty(stride * self.world, dtype=torch.int32, device=self.device)
@@ -105,6 +122,34 @@ class ShardedOrientedBuild:
         return shard.finish(pieces.data_ptr(), stride, self.dplus.data_ptr())
 
 
+class _ShardedArray:
+    """One host array replicated on every rank's device: rank r copies slice r of `world` host->device, one all-gather
+    fills the rest.  The device buffer is padded to a multiple of `world` and reused by every `upload()`."""
+
+    def __init__(self, host, device, rank, world):
+        self.host, self.rank, self.world = host, rank, world
+        self.len = host.numel()
+        self.per = _slice_len(self.len, world)
+        self.full = torch.empty(self.per * world, dtype=host.dtype, device=device)
+
+    def span(self):
+        lo = min(self.rank * self.per, self.len)
+        return lo, min(self.per, self.len - lo)
+
+    @property
+    def h2d_bytes(self):
+        return self.span()[1] * self.host.element_size()
+
+    def upload(self):
+        lo, cnt = self.span()
+        mine = self.full.narrow(0, self.rank * self.per, self.per)
+        if cnt:
+            mine.narrow(0, 0, cnt).copy_(self.host.narrow(0, lo, cnt), non_blocking=True)
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.full, mine)
+        return self.full.narrow(0, 0, self.len)
+
+
 def _slice_len(total, world):
     return (total + world - 1) // world
 
@@ -112,35 +157,18 @@ def _slice_len(total, world):
 class ShardedCsrUpload:
     """Replicates a host CSR (pinned int64 offsets[n+1], int32 nbrs[slots]) on every rank's device: rank r copies slice
     r of `world` host->device, one all-gather per array fills the rest (NVLink on GPUs; gloo + CPU tensors in the CPU
-    test).  Buffers are allocated once and reused by every `upload()`; arrays are padded to a multiple of `world`."""
+    test).  Buffers are allocated once and reused by every `upload()`; arrays are padded to a multiple of `world`.
+    (For operators that need the symmetric lists on every device; the triangle path uses ShardedOrientedBuild.)"""
 
     def __init__(self, offsets_host, nbrs_host, device):
         self.rank, self.world = (dist.get_rank(), dist.get_world_size()) if dist.is_initialized() else (0, 1)
-        self.device = torch.device(device)
-        self.host = (offsets_host, nbrs_host)
-        self.lens = (offsets_host.numel(), nbrs_host.numel())
-        self.per = tuple(_slice_len(x, self.world) for x in self.lens)
-        self.full = tuple(torch.empty(p * self.world, dtype=h.dtype, device=self.device)
-                          for p, h in zip(self.per, self.host))
+        self.arrays = [_ShardedArray(h, torch.device(device), self.rank, self.world) for h in (offsets_host, nbrs_host)]
 
     @property
     def h2d_bytes(self):
         """Bytes this rank copies host->device per upload."""
-        return sum(self._span(i)[1] * self.host[i].element_size() for i in range(2))
-
-    def _span(self, i):
-        lo = min(self.rank * self.per[i], self.lens[i])
-        return lo, min(self.per[i], self.lens[i] - lo)
+        return sum(a.h2d_bytes for a in self.arrays)
 
     def upload(self):
         """Returns (offsets_dev, nbrs_dev) views of the replicated arrays (valid until the next upload)."""
-        outs = []
-        for i in range(2):
-            lo, cnt = self._span(i)
-            mine = self.full[i].narrow(0, self.rank * self.per[i], self.per[i])
-            if cnt:
-                mine.narrow(0, 0, cnt).copy_(self.host[i].narrow(0, lo, cnt), non_blocking=True)
-            if self.world > 1:
-                dist.all_gather_into_tensor(self.full[i], mine)
-            outs.append(self.full[i].narrow(0, 0, self.lens[i]))
-        return tuple(outs)
+        return tuple(a.upload() for a in self.arrays)

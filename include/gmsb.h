@@ -97,7 +97,10 @@ GMSB_API int gmsb_graph_from_csr_ex(int64_t n, const int64_t *offsets, const int
  * orients one vertex range and the finished rows are exchanged instead of the host arrays being read N times.
  *   gmsb_shard_begin   device part_index of part_count uploads the offsets and the neighbour slots of its vertex range
  *                      (ranges of equal slot counts), ranks the vertices (PpParallel::getDegreeOrdering), keeps each
- *                      row's higher-ranked neighbours, relabelled and sorted; *piece_len = entries of its piece
+ *                      row's higher-ranked neighbours, relabelled and sorted; *piece_len = entries of its piece.
+ *                      offsets_dev (may be NULL): the complete offsets already on this device — a caller that uploads
+ *                      1/part_count of them per device and all-gathers saves (part_count - 1) x 8(n+1) bytes of host
+ *                      traffic; `offsets` (host) is then read at a handful of positions only
  *   gmsb_shard_export  writes the piece (rows packed in original-id order) to piece_dev and d+ of the range's vertices
  *                      to dplus_all_dev[range] (an int32[n] the caller zeroed)
  *   (caller)           all-gather of the pieces into pieces_dev[part * piece_stride ...], piece_stride >= every
@@ -106,8 +109,8 @@ GMSB_API int gmsb_graph_from_csr_ex(int64_t n, const int64_t *offsets, const int
  *                      size queries — its symmetric lists are incomplete, every other operator returns GMSB_ERR_INVALID
  * Lists longer than 8192 after orientation are not supported here (GMSB_ERR_INVALID): use gmsb_graph_from_csr_ex. */
 typedef struct gmsb_shard_s *gmsb_shard_t;
-GMSB_API int gmsb_shard_begin(int64_t n, const int64_t *offsets, const int32_t *nbrs, int part_index, int part_count,
-                              gmsb_shard_t *out, int64_t *piece_len);
+GMSB_API int gmsb_shard_begin(int64_t n, const int64_t *offsets, const int32_t *nbrs, const int64_t *offsets_dev,
+                              int part_index, int part_count, gmsb_shard_t *out, int64_t *piece_len);
 GMSB_API int gmsb_shard_export(gmsb_shard_t s, int32_t *piece_dev, int32_t *dplus_all_dev);
 GMSB_API int gmsb_shard_finish(gmsb_shard_t s, const int32_t *pieces_dev, int64_t piece_stride, const int32_t *dplus_all_dev,
                                gmsb_graph_t *out);

@@ -102,9 +102,15 @@ class NumpyShard:
     the own range oriented by (degree, id) rank and packed in original-id order, rows of all pieces moved into rank order
     with  start(u) = scan[u] - scan[cut[r]] + r * stride."""
 
-    def __init__(self, off, nbr, part, parts):
+    def __init__(self, off, nbr, part, parts, offsets_dev_ptr=None):
         self.off, self.nbr, self.part, self.parts = off, nbr, part, parts
         n = self.n = len(off) - 1
+        if offsets_dev_ptr is not None:                 # the all-gathered copy of the offsets: must equal the host's
+            import ctypes
+            got = np.ctypeslib.as_array((ctypes.c_int64 * (n + 1)).from_address(offsets_dev_ptr))
+            assert np.array_equal(got, off)
+        else:
+            assert parts == 1
         last = int(off[n])
         self.cut = [0]
         for i in range(1, parts):

@@ -12,11 +12,14 @@ from conftest import random_graph_edges
 pytestmark = pytest.mark.gpu
 
 
-def build_sharded(gms, off, nbr, parts):
+def build_sharded(gms, off, nbr, parts, device_offsets=False):
     import torch
     dev = torch.device("cuda", 0)
     n = len(off) - 1
-    shards = [gms.capi.Shard(off, nbr, p, parts) for p in range(parts)]
+    off_dev = torch.from_numpy(np.ascontiguousarray(off, np.int64)).to(dev) if device_offsets else None
+    torch.cuda.synchronize()
+    shards = [gms.capi.Shard(off, nbr, p, parts, offsets_dev_ptr=off_dev.data_ptr() if device_offsets else None)
+              for p in range(parts)]
     stride = max(max(s.piece_len for s in shards), 1)
     pieces = torch.full((parts * stride,), -7, dtype=torch.int32, device=dev)        # padding must never be read
     dplus = torch.zeros(max(n, 1), dtype=torch.int32, device=dev)
@@ -32,8 +35,8 @@ def check_against_plain(gms, src, dst, parts_list):
     off, nbr = g.export_csr()
     want, st = g.tc_total_ex(reuse_plan=True)
     want_v2 = g.tc_vertex2() if g.n else None
-    for parts in parts_list:
-        graphs, m = build_sharded(gms, off, nbr, parts)
+    for i, parts in enumerate(parts_list):
+        graphs, m = build_sharded(gms, off, nbr, parts, device_offsets=bool(i % 2))    # offsets from the host / the device
         assert m == st["oriented_edges"]
         for p, gs in enumerate(graphs):
             assert (gs.n, gs.slots, gs.directed) == (g.n, g.slots, False)
