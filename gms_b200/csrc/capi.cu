@@ -367,7 +367,7 @@ GMSB_API int gmsb_graph_worth_relabelling(gmsb_graph_t g, int *out) {
         // host-side heuristic on the degree array (gapbs/benchmark.h:158-176); same libstdc++ RNG stream as the reference
         *out = 0;
         const int64_t n = gr.n;
-        if (n == 0 || (gr.slots / 2) / n < 10) return;
+        if (n == 0 || (gr.directed ? gr.slots : gr.slots / 2) / n < 10) return;      // CSRGraph::num_edges() / num_nodes()
         std::vector<eid_t> off(n + 1);
         gr.off.download(off.data(), n + 1);
         std::mt19937 rng(27491095);

@@ -187,8 +187,8 @@ Graph relabel_by_degree(const Graph &g) {
 
 // WorthRelabelling (gms/third_party/gapbs/benchmark.h:158-176, SourcePicker :51-75).
 bool worth_relabelling(const Graph &g) {
-    int64_t undirected_edges = g.off[g.n] / 2;
-    if (undirected_edges / g.n < 10) return false;
+    int64_t num_edges = g.directed ? g.off[g.n] : g.off[g.n] / 2;      // CSRGraph::num_edges()
+    if (num_edges / g.n < 10) return false;
     std::mt19937 rng(kSeed);
     std::uniform_int_distribution<vid> pick(0, (vid)(g.n - 1));
     int64_t ns = std::min<int64_t>(1000, g.n), total = 0;
