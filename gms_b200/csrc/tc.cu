@@ -378,7 +378,7 @@ k_plan_scatter_flat(const vid_t *__restrict__ nbr, const uint32_t *__restrict__ 
 // the slice's first long suffix actually starts in the neighbour array (every device orders its own share now).
 constexpr int kNearWords = kSmallWindowBytes / 4 - 1;
 __global__ void k_item_keys(const Item *__restrict__ items, int64_t cnt, int64_t n, int64_t ntiles, int addr_shift,
-                            const uint64_t *__restrict__ desc,
+                            int vbits, int tbits, const uint64_t *__restrict__ desc,
                             const int64_t *__restrict__ nitems, const int64_t *__restrict__ item_base,
                             const eid_t *__restrict__ off, const vid_t *__restrict__ nbr,
                             uint64_t *__restrict__ keys, unsigned long long *__restrict__ cls_count /* 3 */,
@@ -399,7 +399,9 @@ __global__ void k_item_keys(const Item *__restrict__ items, int64_t cnt, int64_t
         if (reach_words <= kNearWords) { cls = 0; words = (int)reach_words; }
         atomicAdd(&cls_count[cls], 1ull);
         atomicMax(&cls_words[cls], words);
-        keys[i] = ((uint64_t)cls << 62) | ((tile & 0x3fffffffull) << 32) | (uint64_t)(uint32_t)(n - 1 - it.v);
+        // packed into as few bits as the graph needs: the radix sort below runs one pass per 8 key bits
+        keys[i] = ((uint64_t)cls << (tbits + vbits)) | ((tile & ((1ull << tbits) - 1ull)) << vbits) |
+                  (uint64_t)(uint32_t)(n - 1 - it.v);
     }
 }
 
@@ -854,8 +856,11 @@ TcPlan *build_plan(Dag &d, const gmsb_tc_options &opt) {
             DevBuf<unsigned long long> ccnt(3);
             DevBuf<int> cwords(3);
             ccnt.zero(); cwords.zero();
-            k_item_keys<<<grid_for(p->n_items, 256), 256, 0, r.stream>>>(p->items.p, p->n_items, n, ntiles, addr_shift,
-                                                                        p->desc.p, nitems.p, item_base.p, d.off.p,
+            const int vbits = bits_for((uint64_t)n);
+            const int tbits = bits_for((uint64_t)(addr_shift > 0 ? (m >> addr_shift) : ntiles - 1));
+            const int key_bits = 2 + tbits + vbits;                 // class | tile | n - 1 - v
+            k_item_keys<<<grid_for(p->n_items, 256), 256, 0, r.stream>>>(p->items.p, p->n_items, n, ntiles, addr_shift, vbits,
+                                                                        tbits, p->desc.p, nitems.p, item_base.p, d.off.p,
                                                                         d.nbr.p, ik.p, ccnt.p, cwords.p);
             launched();
             unsigned long long h_cc[3];
@@ -864,11 +869,11 @@ TcPlan *build_plan(Dag &d, const gmsb_tc_options &opt) {
             for (int c = 0; c < 3; ++c) p->cls_items[c] = (int64_t)h_cc[c];
             size_t bytes = 0;
             GMSB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, ik.p, ik2.p, p->items.p, items2.p, p->n_items, 0,
-                                                      64, r.stream));
+                                                      key_bits, r.stream));
             DevBuf<uint8_t> tmp(bytes);
             GMSB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, ik.p, ik2.p, p->items.p, items2.p, p->n_items, 0,
-                                                      64, r.stream));
-            r.launches += 9;
+                                                      key_bits, r.stream));
+            r.launches += (uint64_t)((key_bits + 7) / 8 + 1);
             GMSB_CUDA(cudaStreamSynchronize(r.stream));
             p->items = std::move(items2);
         }
