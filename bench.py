@@ -11,8 +11,9 @@ symmetric CSR on the GPU (radix sort), keep a copy of the CSR in PINNED host mem
                items, light lists) is specific to this kernel, so it is rebuilt INSIDE every timed step
                (gmsb_tc_options.reuse_plan = 2): a step = schedule build + every counting kernel over all oriented
                edges + the count back (checked every step).  `count_only` is the same without the schedule build;
-  * `e2e`    : K steps of the call a user makes from host memory: gmsb_graph_from_csr (pinned host CSR -> HBM) +
-               gmsb_tc_total_ex (orient + schedule + count, nothing cached) + the 8-byte result back + free;
+  * `e2e`    : K steps of the call a user makes from host memory: gmsb_graph_from_csr_ex(GMSB_BUILD_ORIENT) (pinned host
+               CSR -> HBM, orientation pipelined with the upload) + gmsb_tc_total_ex (schedule + count, nothing
+               cached) + the 8-byte result back + free;
   * `roofline`: the dominant kernel (k_tc_bitmap) — its algorithmic bytes / its CUDA-event time, vs MEASURED_PEAKS;
   * `cpu_baseline` (N=1): the reference's own Par::count_total inner loop (oracle/_ref, else the oracle port) on a
                bounded sample of the same graph, all host threads;
@@ -20,9 +21,10 @@ symmetric CSR on the GPU (radix sort), keep a copy of the CSR in PINNED host mem
                (Kronecker scale-22), sub-problems dealt over the ranks, one all-reduce (--kclique '' skips it); at N=1
                with `kclique.cpu_baseline`: the reference's Par::EP_kclisting on all host threads on Kronecker
                scale-16 and our kernels on that same graph.
-N>1 (torchrun): every rank holds the whole CSR, counts share rank/N of the schedule, one all-reduce sums the counts;
-time = max over ranks.  In the e2e leg rank r uploads slice r/N of the host CSR and the slices are all-gathered over
-NVLink, so h2d_bytes_per_step is still the whole CSR once (summed over ranks).
+N>1 (torchrun): every rank holds the graph, builds and counts only ITS share of the schedule (the edges whose closing
+vertex it owns), one all-reduce sums the counts; time = max over ranks.  In the e2e leg rank r uploads 1/N of the offsets
+and the neighbour slots of vertex range r, orients that range, and the finished rows are all-gathered over NVLink
+(gmsb_shard_*), so h2d_bytes_per_step is still the whole CSR once (summed over ranks).
 
 Reference arm (--impl reference): rank 0 only, the reference's CPU path on bounded samples of the same workload.
 """
@@ -436,7 +438,7 @@ def run_ours(args):
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "int32", "data": "synthetic",
         "config": {"workload": f"triangle counting, {family} scale-{args.scale} edge factor 16 (n={n}, m={m})",
-                   "variant": args.variant, "parallelism": f"edge-partition x{world}, CSR replicated",
+                   "variant": args.variant, "parallelism": f"edge-partition x{world} by closing vertex, schedule built per share",
                    "l2": "inputs_exceed_L2 (oriented CSR %.2f GB vs 126 MB L2)" % (st["oriented_edges"] * 4 / 1e9),
                    "step": "schedule build + count_total over the oriented device graph (DAG built once, dag_ms); "
                            "everything from the host CSR on is in e2e"},

@@ -4,7 +4,8 @@
 // gmsb_set_devices(8, ids) once and then the *_multi entry points with the handle it already has:
 //   * the graph's CSR is replicated to the other devices over NVLink (cudaMemcpyPeer, cached on the handle);
 //   * one host thread per device runs the partitioned form of the kernel on its replica (the same part_index /
-//     part_count partition the torchrun path uses: schedule items, light edges and clique sub-problems dealt round-robin);
+//     part_count partition the torchrun path uses: edges by the owner of their closing vertex, clique sub-problems dealt
+//     round-robin);
 //   * scalar results (triangle / clique counts) are summed on the host — eight 8-byte values need no collective —
 //     while array results go through NCCL: vertex_count2 is one ncclAllReduce(int64[n]) of the per-vertex partial sums,
 //     the per-edge similarity one ncclAllReduce(uint32[m]) of the partial edge supports, after which every device scores

@@ -1,12 +1,13 @@
-"""Multi-GPU plumbing: one process per GPU, oriented edges partitioned, CSR replicated, one all-reduce of the counts.
+"""Multi-GPU plumbing: one process per GPU, oriented edges partitioned, one all-reduce of the counts.
 
-The path shards with no data-path collective: every rank builds the same graph, takes share
-`rank` of `world` of the schedule (gmsb_tc_options.part_index / part_count) and the uint64 partial counts are
-summed by a single all-reduce (NCCL over NVLink on GPUs, gloo in the CPU tests).
+Counting shards with no data-path collective: every rank takes share `rank` of `world` of the edges
+(gmsb_tc_options.part_index / part_count: those whose closing vertex it owns; it builds the schedule of that share
+only) and the uint64 partial counts are summed by a single all-reduce (NCCL over NVLink on GPUs, gloo in the CPU tests).
 
-Replicating the CSR from HOST memory is the one place a collective pays: instead of every rank pulling the whole
-2.2 GB over its own PCIe link from the same host DRAM, rank r uploads slice r of N and the slices are all-gathered
-over NVLink (`ShardedCsrUpload`), so the host is read once.
+Getting a HOST CSR onto N devices is where collectives pay: `ShardedOrientedBuild` has every rank upload and orient one
+vertex range and all-gathers the finished rows of the oriented representation (what the triangle kernels read);
+`ShardedCsrUpload` replicates the symmetric arrays themselves (rank r uploads slice r of N, one all-gather per array) for
+the operators that need them.  Either way the host is read once, not N times.
 """
 import os
 
